@@ -1,0 +1,321 @@
+"""Oracle (test infrastructure): write tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (``python -m oracle.make_golden``): it imports
+``utils``, ``config`` and ``genData.player.Player`` from ``/root/reference`` and
+records their outputs on seeded inputs.  ``/root/reference`` does not exist on the
+GPU box, so the tests read only the committed ``.npz`` files.
+
+Fixtures
+--------
+rules_{S}.npz        boards + what utils.is_game_over / board_to_state / step /
+                     get_legal_actions / board_to_inputs return for them
+mcts_kat_{S}.npz     deterministic Player(training=False) root statistics after k
+                     simulations under oracle.mcts.table_pv_fn (tie-free, checked)
+mcts_game_{S}.npz    a multi-move deterministic game with tree reuse (budget rule
+                     player.py:140-143, retained sub-tree statistics)
+mcts_train_11.npz    seeded training-mode summary statistics (distributional pins)
+replay_sample.npz    1,024 records + 3 whole games of data_buffer/data6960.pkl
+ckpt6960.npz         the 42 tensors of ckpt/alphaFive-6960 (via alphafive_b200.ckpt)
+weights.npz          construct_weights(L, 0.94) for L = 1..64
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import random
+import sys
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _ref():
+    sys.path.insert(0, REF)
+    import config  # noqa
+    import utils  # noqa
+    from genData.player import Player  # noqa
+    return utils, config, Player
+
+
+def _code(over, v):
+    return 0 if not over else 1 if v > 0 else 2 if v < 0 else 3
+
+
+def adversarial_boards(S, rng):
+    """Fives of both colours, overlines, edge-clipped runs, full boards."""
+    out = []
+    for _ in range(300):
+        b = np.zeros((S, S), np.int8)
+        for _ in range(rng.integers(1, 4)):
+            colour = rng.choice([-1, 1])
+            length = int(rng.integers(4, 8))
+            d = [(1, 0), (0, 1), (1, 1), (-1, 1)][rng.integers(0, 4)]
+            i, j = int(rng.integers(0, S)), int(rng.integers(0, S))
+            for k in range(length):
+                ii, jj = i + d[0] * k, j + d[1] * k
+                if 0 <= ii < S and 0 <= jj < S:
+                    b[ii, jj] = colour
+        noise = rng.random((S, S))
+        b[(b == 0) & (noise < 0.15)] = 1
+        b[(b == 0) & (noise > 0.85)] = -1
+        out.append(b)
+    for _ in range(60):                                   # full / nearly full boards
+        b = rng.choice(np.array([-1, 1], np.int8), size=(S, S))
+        # checker-ish pattern breaks most fives so that draws actually occur
+        if rng.random() < 0.7:
+            base = np.fromfunction(lambda i, j: ((i // 2 + j) % 2) * 2 - 1, (S, S)).astype(np.int8)
+            flip = rng.random((S, S)) < 0.03
+            b = np.where(flip, -base, base).astype(np.int8)
+        if rng.random() < 0.5:
+            b[rng.integers(0, S), rng.integers(0, S)] = 0
+        out.append(b)
+    return out
+
+
+def make_rules(S, utils, n_random, seed):
+    from oracle import rules
+    rng = np.random.default_rng(seed)
+    boards = [rules.random_board(rng, S) for _ in range(n_random)]
+    boards += adversarial_boards(S, rng)
+    boards.append(np.zeros((S, S), np.int8))
+    boards = np.stack(boards).astype(np.int8)
+    N = boards.shape[0]
+    codes = np.zeros(N, np.int8)
+    states = []
+    acts = np.zeros((N, 2), np.int16)
+    last = np.full((N, 2), -1, np.int16)
+    stepped = np.zeros_like(boards)
+    inputs = np.zeros((N, 3, S, S), np.int8)
+    nlegal = np.zeros(N, np.int16)
+    for t in range(N):
+        b = boards[t]
+        codes[t] = _code(*utils.is_game_over(b.copy(), 5))
+        s = utils.board_to_state(b)
+        assert (utils.state_to_board(s, S) == b).all()
+        states.append(s)
+        legal = utils.get_legal_actions(b)
+        nlegal[t] = len(legal)
+        la = None
+        if rng.random() < 0.8:
+            la = (int(rng.integers(0, S)), int(rng.integers(0, S)))
+            last[t] = la
+        inputs[t] = utils.board_to_inputs(b, last_action=la).astype(np.int8)
+        if legal:
+            a = legal[int(rng.integers(0, len(legal)))]
+            acts[t] = a
+            stepped[t] = utils.step(b.copy(), a)
+        else:
+            acts[t] = (-1, -1)
+            stepped[t] = b
+    np.savez_compressed(os.path.join(OUT, f"rules_{S}.npz"), boards=boards, codes=codes,
+                        states=np.array(states), actions=acts, stepped=stepped,
+                        last_action=last, inputs=inputs, nlegal=nlegal)
+    print(f"rules_{S}: {N} boards; codes", np.bincount(codes, minlength=4))
+
+
+class _TieWatch:
+    """Wraps np.random.choice / random.choice to prove a run never had to break a tie."""
+
+    def __init__(self):
+        self.worst = 1          # ties inside the search (np.random.choice, player.py:278)
+        self.worst_final = 1    # ties in the final most-visited pick (random.choice, player.py:102)
+
+    def __enter__(self):
+        self._np, self._py = np.random.choice, random.choice
+
+        def np_choice(a, *args, **kw):
+            if kw.get("p") is None and not args:
+                self.worst = max(self.worst, len(a) if hasattr(a, "__len__") else 1)
+            return self._np(a, *args, **kw)
+
+        def py_choice(seq):
+            self.worst_final = max(self.worst_final, len(seq))
+            return self._py(seq)
+
+        np.random.choice, random.choice = np_choice, py_choice
+        return self
+
+    def __exit__(self, *exc):
+        np.random.choice, random.choice = self._np, self._py
+
+
+def _root_arrays(player, state, S):
+    node = player.tree[state]
+    n = np.zeros(S * S, np.int32)
+    w = np.zeros(S * S, np.float32)
+    p = np.zeros(S * S, np.float32)
+    for (i, j), e in node.a.items():
+        n[i * S + j], w[i * S + j], p[i * S + j] = e.n, e.w, e.p
+    return n, w, p, node.sum_n
+
+
+def make_mcts_kat(S, utils, config, Player, roots, ks, salt):
+    from oracle.mcts import table_pv_fn
+    config.board_size = S
+    pv = table_pv_fn(S, salt)
+    rec = dict(root_boards=[], root_last=[], k=[], n=[], w=[], p=[], sum_n=[], action=[], nkeys=[],
+               key_boards=[], key_sum_n=[], key_off=[0])
+    for board, la in roots:
+        for k in ks:
+            config.simulation_per_step = k
+            config.upper_simulation_per_step = k + 100
+            pl = Player(config, training=False, pv_fn=pv)
+            state = utils.board_to_state(board)
+            with _TieWatch() as tw:
+                _, action = pl.get_action(state, last_action=la)
+            assert tw.worst == 1, f"tie encountered (S={S}, k={k})"
+            if tw.worst_final > 1:          # e.g. k = 1: no edge visited yet, the pick is random
+                action = (-1, -1)
+            n, w, p, sum_n = _root_arrays(pl, state, S)
+            rec["root_boards"].append(board); rec["root_last"].append(la if la else (-1, -1))
+            rec["k"].append(k); rec["n"].append(n); rec["w"].append(w); rec["p"].append(p)
+            rec["sum_n"].append(sum_n); rec["action"].append(action); rec["nkeys"].append(len(pl.tree))
+            keys = sorted(pl.tree.keys())
+            rec["key_boards"].extend(utils.state_to_board(s, S) for s in keys)
+            rec["key_sum_n"].extend(pl.tree[s].sum_n for s in keys)
+            rec["key_off"].append(len(rec["key_boards"]))
+    np.savez_compressed(os.path.join(OUT, f"mcts_kat_{S}.npz"), salt=salt,
+                        **{k: np.asarray(v) for k, v in rec.items()})
+    print(f"mcts_kat_{S}: {len(rec['k'])} cases, {len(rec['key_boards'])} table keys")
+
+
+def make_mcts_game(S, utils, config, Player, sims, upper, plies, salt):
+    """Tries successive salts until the whole game is tie-free (visit-count ties in the
+    final pick are common at low simulation counts)."""
+    from oracle.mcts import table_pv_fn
+    config.board_size = S
+    config.simulation_per_step, config.upper_simulation_per_step = sims, upper
+    for salt in range(salt, salt + 200):
+        pl = Player(config, training=False, pv_fn=table_pv_fn(S, salt))
+        state, action = pl.get_init_state(), None
+        rec = dict(boards=[], last=[], n=[], w=[], sum_n=[], action=[], budget=[], nkeys=[])
+        with _TieWatch() as tw:
+            for _ in range(plies):
+                seen = state in pl.tree
+                budget = sims if not seen else min(sims, upper - pl.tree[state].sum_n)
+                la = action
+                _, action = pl.get_action(state, last_action=la)
+                n, w, _, sum_n = _root_arrays(pl, state, S)
+                board = utils.state_to_board(state, S)
+                rec["boards"].append(board.copy()); rec["last"].append(la if la else (-1, -1))
+                rec["n"].append(n); rec["w"].append(w); rec["sum_n"].append(sum_n)
+                rec["action"].append(action); rec["budget"].append(budget); rec["nkeys"].append(len(pl.tree))
+                board = utils.step(board, action)
+                state = utils.board_to_state(board)
+                if utils.is_game_over(board, 5)[0] or tw.worst > 1 or tw.worst_final > 1:
+                    break
+        if tw.worst == 1 and tw.worst_final == 1:
+            break
+    else:
+        raise AssertionError("no tie-free salt found for the game KAT")
+    np.savez_compressed(os.path.join(OUT, f"mcts_game_{S}.npz"), salt=salt, sims=sims, upper=upper,
+                        **{k: np.asarray(v) for k, v in rec.items()})
+    print(f"mcts_game_{S}: salt {salt}, {len(rec['action'])} plies, budgets {rec['budget']}")
+
+
+def make_mcts_train(utils, config, Player, salt):
+    """Seeded summary statistics of training-mode searches (Dirichlet noise at every
+    node visit, forced-visit ladder at the root): distributional pins."""
+    from oracle.mcts import table_pv_fn
+    S = 11
+    config.board_size = S
+    config.simulation_per_step, config.upper_simulation_per_step = 300, 400
+    np.random.seed(1234); random.seed(1234)
+    runs = 64
+    ns = np.zeros((runs, S * S), np.int32)
+    depth = np.zeros(runs)
+    for r in range(runs):
+        pl = Player(config, training=True, pv_fn=table_pv_fn(S, salt))
+        state = pl.get_init_state()
+        pl.root_state = state                     # what get_action does first (player.py:138)
+        for _ in range(300):
+            pl.MCTS_search(state, [state], None)
+        ns[r] = _root_arrays(pl, state, S)[0]
+        depth[r] = sum(st.sum_n for st in pl.tree.values()) / 300.0
+    np.savez_compressed(os.path.join(OUT, "mcts_train_11.npz"), salt=salt, sims=300, n=ns, depth=depth)
+    print("mcts_train_11: min visits", ns.min(), "mean max", ns.max(1).mean(), "depth", depth.mean())
+
+
+def make_replay(utils):
+    data = pickle.load(open(f"{REF}/data_buffer/data6960.pkl", "rb"))
+    lens = pickle.load(open(f"{REF}/data_buffer/data_len6960.pkl", "rb"))
+    res = pickle.load(open(f"{REF}/data_buffer/result6960.pkl", "rb"))
+    total = int(np.sum(lens))
+    start0 = len(data) - total                    # game 0 may be front-truncated (utils.py:101-115)
+    offs = np.concatenate([[0], np.cumsum(lens)]) + start0
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(len(data), 1024, replace=False))
+    games = [5, 123, 400]
+    idx = list(pick)
+    game_off = [0]
+    gidx = []
+    for g in games:
+        gidx.extend(range(int(offs[g]), int(offs[g + 1])))
+        game_off.append(len(gidx))
+
+    def pack(ix):
+        S = 11
+        boards = np.stack([utils.state_to_board(data[i][0], S) for i in ix]).astype(np.int8)
+        pol = np.stack([data[i][1] for i in ix]).astype(np.float32)
+        la = np.array([data[i][2] if data[i][2] is not None else (-1, -1) for i in ix], np.int16)
+        val = np.array([data[i][3] for i in ix], np.float32)
+        wt = np.array([data[i][4] for i in ix], np.float32)
+        st = np.array([data[i][0] for i in ix])
+        return boards, pol, la, val, wt, st
+
+    b, p, la, v, w, s = pack(idx)
+    gb, gp, gla, gv, gw, gs = pack(gidx)
+    np.savez_compressed(os.path.join(OUT, "replay_sample.npz"), boards=b, policy=p, last_action=la,
+                        value=v, weight=w, states=s,
+                        g_boards=gb, g_policy=gp, g_last_action=gla, g_value=gv, g_weight=gw,
+                        g_states=gs, g_off=np.array(game_off), g_result=np.array([res[g] for g in games]),
+                        logged_losses=np.array([2.155, 0.313, 2.145], np.float32))
+    print("replay_sample: 1024 records +", len(gidx), "records of 3 games")
+
+
+def make_ckpt():
+    from alphafive_b200 import ckpt
+    w = ckpt.read_bundle(f"{REF}/ckpt")
+    np.savez_compressed(os.path.join(OUT, "ckpt6960.npz"), **{k.replace("/", "__"): v for k, v in w.items()})
+    print("ckpt6960:", len(w), "tensors", sum(v.size for v in w.values()), "params")
+
+
+def make_weights(utils):
+    L = np.arange(1, 65)
+    ws = np.zeros((64, 64), np.float32)
+    for l in L:
+        ws[l - 1, :l] = utils.construct_weights(int(l), gamma=0.94)
+    np.savez_compressed(os.path.join(OUT, "weights.npz"), w=ws)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    utils, config, Player = _ref()
+    if "--mcts-only" not in sys.argv:
+        make_rules(11, utils, 3000, 11)
+        make_rules(15, utils, 1500, 15)
+        make_weights(utils)
+        make_replay(utils)
+        make_ckpt()
+    rs = np.load(os.path.join(OUT, "replay_sample.npz"))
+    roots11 = [(np.zeros((11, 11), np.int8), None)]
+    for t in (40, 333, 800):
+        la = tuple(int(x) for x in rs["last_action"][t])
+        roots11.append((rs["boards"][t].copy(), la if la[0] >= 0 else None))
+    make_mcts_kat(11, utils, config, Player, roots11, [1, 2, 10, 100, 500], salt=3)
+    rng = np.random.default_rng(5)
+    from oracle import rules
+    mid15 = rules.random_board(rng, 15, 0.12)
+    while rules.terminal(mid15)[0]:
+        mid15 = rules.random_board(rng, 15, 0.12)
+    make_mcts_kat(15, utils, config, Player, [(np.zeros((15, 15), np.int8), None), (mid15, (7, 7))],
+                  [1, 10, 120], salt=4)
+    make_mcts_game(11, utils, config, Player, sims=120, upper=135, plies=14, salt=5)
+    make_mcts_game(15, utils, config, Player, sims=60, upper=68, plies=8, salt=6)
+    make_mcts_train(utils, config, Player, salt=9)
+
+
+if __name__ == "__main__":
+    main()
