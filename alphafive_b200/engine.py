@@ -1,0 +1,204 @@
+"""SearchEngine: N concurrent MCTS games on the device (a5_engine_*).
+
+Python mirror of the reference's search loop for many games at once: the object plays
+the role of N ``genData.player.Player`` instances stepping in lock-step."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, RecordHeader, check, ptr, stream_ptr
+
+COUNTER_NAMES = ("moves", "sims", "leaf_evals", "terminal_leaves", "selects", "legal_sum", "games",
+                 "max_nodes", "overflows", "passes", "records_dropped")
+
+
+def make_config(cfg=None, **kw) -> Config:
+    """a5_config from a reference-style config module/object (config.py attribute names)."""
+    g = lambda name, default: kw.pop(name, getattr(cfg, name, default) if cfg is not None else default)
+    c = Config()
+    c.board_size = g("board_size", 11)
+    c.goal = g("goal", 5)
+    c.sims = g("simulation_per_step", 542)
+    c.upper_sims = g("upper_simulation_per_step", 642)
+    c.c_puct = g("c_puct", 5.0)
+    c.dirichlet_alpha = g("dirichlet_alpha", 0.3)
+    c.init_temp = g("init_temp", 1.2)
+    c.tau_decay = g("tau_decay_rate", 0.94)
+    c.tau_decay_r = g("tau_decay_rate_r", 0.9)
+    c.gamma = g("gamma", 0.94)
+    c.n_games = kw.pop("n_games", 1)
+    c.training = int(kw.pop("training", True))
+    c.random_a = int(kw.pop("random_a", False))
+    c.auto_play = int(kw.pop("auto_play", False))
+    c.node_capacity = kw.pop("node_capacity", 0)
+    c.max_inner = kw.pop("max_inner", 0)
+    c.seed = kw.pop("seed", 0)
+    c.game_id_base = kw.pop("game_id_base", 0)
+    c.record_capacity = kw.pop("record_capacity", 0)
+    assert not kw, f"unknown config keys {sorted(kw)}"
+    return c
+
+
+class SearchEngine:
+    def __init__(self, config: Config, device=None):
+        self.lib = _lib.load()
+        self.cfg = config
+        self.N, self.S = config.n_games, config.board_size
+        self.C = self.S * self.S
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.a5_engine_create(C.byref(config), C.byref(h)))
+        self.handle = h
+        self.planes_ptr = self.lib.a5_engine_planes(h)
+        self.record_stride = self.lib.a5_record_stride(self.S)
+        self._first = True
+
+    # -- raw passes -----------------------------------------------------------
+    def reset(self):
+        check(self.lib.a5_engine_reset(self.handle, stream_ptr()))
+        self._first = True
+
+    def set_roots(self, boards, last=None, active=None, clear=None):
+        """boards int8[N,S,S]; last int32[N] flat cell or -1; active/clear uint8[N]."""
+        dev = self.device
+        boards = torch.as_tensor(boards, dtype=torch.int8).to(dev).contiguous()
+        last_t = None if last is None else torch.as_tensor(last, dtype=torch.int32).to(dev).contiguous()
+        act_t = None if active is None else torch.as_tensor(active, dtype=torch.uint8).to(dev).contiguous()
+        clr_t = None if clear is None else torch.as_tensor(clear, dtype=torch.uint8).to(dev).contiguous()
+        check(self.lib.a5_engine_set_roots(self.handle, ptr(boards), ptr(last_t), ptr(act_t), ptr(clr_t), stream_ptr()))
+        self._first = True
+
+    def step(self, prob=None, value=None):
+        if self._first:
+            prob = value = None
+            self._first = False
+        check(self.lib.a5_engine_step(self.handle, ptr(prob), ptr(value), stream_ptr()))
+
+    def planes(self) -> torch.Tensor:
+        """Zero-copy int8 [N,3,S,S] view of the leaf planes written by the last pass."""
+        return _view(self.planes_ptr, (self.N, 3, self.S, self.S), torch.int8, self.device)
+
+    def need_eval(self) -> torch.Tensor:
+        return _view(self.lib.a5_engine_need_eval(self.handle), (self.N,), torch.uint8, self.device)
+
+    def sims_left(self) -> torch.Tensor:
+        return _view(self.lib.a5_engine_sims_left(self.handle), (self.N,), torch.int32, self.device)
+
+    def busy(self) -> int:
+        b = C.c_int32()
+        check(self.lib.a5_engine_busy(self.handle, C.byref(b), stream_ptr()))
+        return b.value
+
+    def finish_move(self):
+        policy = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        action = torch.empty((self.N,), dtype=torch.int32, device=self.device)
+        check(self.lib.a5_engine_finish_move(self.handle, ptr(policy), ptr(action), stream_ptr()))
+        return policy, action
+
+    def root_stats(self):
+        n = torch.empty((self.N, self.C), dtype=torch.int32, device=self.device)
+        w = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        p = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        s = torch.empty((self.N,), dtype=torch.int32, device=self.device)
+        check(self.lib.a5_engine_root_stats(self.handle, ptr(n), ptr(w), ptr(p), ptr(s), stream_ptr()))
+        return n, w, p, s
+
+    def table_dump(self, game: int, max_nodes: int = 65536):
+        boards = torch.empty((max_nodes, self.S, self.S), dtype=torch.int8, device=self.device)
+        sums = torch.empty((max_nodes,), dtype=torch.int32, device=self.device)
+        cnt = C.c_int32()
+        check(self.lib.a5_engine_table_dump(self.handle, game, ptr(boards), ptr(sums), max_nodes, C.byref(cnt), stream_ptr()))
+        k = min(cnt.value, max_nodes)
+        return boards[:k].cpu().numpy(), sums[:k].cpu().numpy()
+
+    def counters(self) -> dict:
+        arr = (C.c_int64 * _lib.NUM_COUNTERS)()
+        check(self.lib.a5_engine_counters(self.handle, arr, stream_ptr()))
+        return {k: int(arr[i]) for i, k in enumerate(COUNTER_NAMES)}
+
+    def harvest(self, buf: torch.Tensor | None = None):
+        """Finished-ply records as a uint8 [count, stride] CUDA tensor + games completed."""
+        cap = self.cfg.record_capacity or self.N * self.C
+        if buf is None:
+            buf = torch.empty((cap, self.record_stride), dtype=torch.uint8, device=self.device)
+        cnt, games = C.c_int32(), C.c_int32()
+        check(self.lib.a5_engine_harvest(self.handle, ptr(buf), buf.shape[0], C.byref(cnt), C.byref(games), stream_ptr()))
+        return buf[:cnt.value], games.value
+
+    # -- convenience: run until every game's budget is spent (auto_play = 0) ------
+    def run_search(self, net=None, pv_fn=None, check_every: int = 16):
+        """Drive step/forward until no game is busy.  ``net`` is a DeviceNet (on-device
+        leaf evaluation); ``pv_fn`` is a reference-style host callable."""
+        assert (net is None) != (pv_fn is None)
+        prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        value = torch.empty((self.N,), dtype=torch.float32, device=self.device)
+        it = 0
+        self.step()
+        while True:
+            if pv_fn is not None:
+                need = self.need_eval().cpu().numpy().astype(bool)
+                if not need.any():
+                    if self.busy() == 0:
+                        break
+                else:
+                    x = self.planes().cpu().numpy().astype(np.float32)
+                    p = np.zeros((self.N, self.C), np.float32)
+                    v = np.zeros((self.N,), np.float32)
+                    idx = np.flatnonzero(need)
+                    pi, vi = pv_fn(x[idx])
+                    p[idx], v[idx] = pi, vi
+                    prob.copy_(torch.from_numpy(p))
+                    value.copy_(torch.from_numpy(v))
+            else:
+                net.forward_raw(self.planes_ptr, self.N, prob, value)
+                it += 1
+                if it % check_every == 0 and self.busy() == 0:
+                    break
+            self.step(prob, value)
+        return it
+
+    def close(self):
+        if self.handle:
+            self.lib.a5_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DevView:
+    """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
+    _TYPES = {torch.int8: "|i1", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4"}
+
+    def __init__(self, p, shape, dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": self._TYPES[dtype],
+                                         "data": (int(p), False), "version": 2}
+
+
+def _view(p, shape, dtype, device) -> torch.Tensor:
+    return torch.as_tensor(_DevView(p, shape, dtype), device=device)
+
+
+def parse_records(buf: torch.Tensor, S: int):
+    """Harvested records -> list of dicts with numpy fields (host side)."""
+    host = buf.cpu().numpy()
+    Cc = S * S
+    bb = (Cc + 15) // 16 * 16
+    hs = C.sizeof(RecordHeader)
+    out = []
+    for row in host:
+        h = RecordHeader.from_buffer_copy(row[:hs].tobytes())
+        board = row[hs:hs + Cc].view(np.int8).reshape(S, S).copy()
+        policy = row[hs + bb:hs + bb + 4 * Cc].view(np.float32).reshape(S, S).copy()
+        out.append(dict(game_id=h.game_id, game_serial=h.game_serial, ply=h.ply, game_len=h.game_len,
+                        last_action=h.last_action, value=h.value, weight=h.weight, result=h.result,
+                        board=board, policy=policy))
+    return out

@@ -162,3 +162,23 @@ def random_board(rng: np.random.Generator, size: int, fill: float | None = None)
     b[u < fill / 2] = 1
     b[(u >= fill / 2) & (u < fill)] = -1
     return b
+
+
+def terminal_codes_batch(boards: np.ndarray, goal: int = 5) -> np.ndarray:
+    """Vectorised :func:`terminal_code` over ``int8[N, S, S]`` (same scan-order rule)."""
+    b = np.asarray(boards).astype(np.int32)
+    N, S, _ = b.shape
+    n = S - goal + 1
+    ws = np.zeros((N, S, S, 4), np.int32)
+    k = range(goal)
+    ws[:, :n, :, 0] = sum(b[:, t:t + n, :] for t in k)
+    ws[:, :, :n, 1] = sum(b[:, :, t:t + n] for t in k)
+    ws[:, :n, :n, 2] = sum(b[:, t:t + n, t:t + n] for t in k)
+    ws[:, goal - 1:, :n, 3] = sum(b[:, goal - 1 - t:goal - 1 - t + n, t:t + n] for t in k)
+    flat = ws.reshape(N, -1)
+    hit = np.abs(flat) == goal
+    first = hit.argmax(1)
+    anyhit = hit.any(1)
+    sign = flat[np.arange(N), first]
+    full = ~(b == 0).reshape(N, -1).any(1)
+    return np.where(anyhit, np.where(sign > 0, 1, 2), np.where(full, 3, 0)).astype(np.int8)

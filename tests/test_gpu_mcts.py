@@ -1,0 +1,194 @@
+"""Device search engine (C ABI) vs golden root statistics of the real reference Player,
+vs the oracle, and self-play record invariants."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import mcts as omcts, rules as orules
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(S, n_games, sims, upper, **kw):
+    from alphafive_b200.engine import SearchEngine, make_config
+    cfg = make_config(board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper,
+                      n_games=n_games, **kw)
+    return SearchEngine(cfg)
+
+
+def _cells(last, S):
+    last = np.asarray(last).astype(np.int64)
+    return np.where(last[:, 0] >= 0, last[:, 0] * S + last[:, 1], -1).astype(np.int32)
+
+
+@pytest.mark.parametrize("S", [11, 15])
+def test_deterministic_known_answers(cuda_lib, S):
+    """training=False search under the tie-free table pv_fn: root n / w / p / sum_n, the
+    chosen move and the whole table (keys + sum_n) equal the reference's, exactly."""
+    g = golden(f"mcts_kat_{S}.npz")
+    pv = omcts.table_pv_fn(S, int(g["salt"]))
+    ks = g["k"]
+    for k in np.unique(ks):
+        idx = np.flatnonzero(ks == k)
+        eng = _engine(S, len(idx), int(k), int(k) + 100, training=False)
+        eng.set_roots(g["root_boards"][idx], _cells(g["root_last"][idx], S))
+        eng.run_search(pv_fn=pv)
+        n, w, p, s = [t.cpu().numpy() for t in eng.root_stats()]
+        _, action = eng.finish_move()
+        action = action.cpu().numpy()
+        for j, t in enumerate(idx):
+            assert (n[j] == g["n"][t].reshape(-1)).all(), (S, k, j)
+            assert s[j] == g["sum_n"][t]
+            assert (w[j] == g["w"][t].reshape(-1)).all()
+            assert (p[j] == g["p"][t].reshape(-1)).all()
+            if g["action"][t][0] >= 0:
+                assert action[j] == g["action"][t][0] * S + g["action"][t][1]
+            boards, sums = eng.table_dump(j)
+            lo, hi = int(g["key_off"][t]), int(g["key_off"][t + 1])
+            want = {g["key_boards"][i].tobytes(): int(g["key_sum_n"][i]) for i in range(lo, hi)}
+            got = {b.tobytes(): int(v) for b, v in zip(boards, sums)}
+            assert got == want
+        c = eng.counters()
+        assert c["overflows"] == 0
+        eng.close()
+
+
+@pytest.mark.parametrize("S", [11, 15])
+def test_deterministic_game_with_tree_reuse(cuda_lib, S):
+    """get_action move after move on one engine: retained sub-tree statistics, the
+    budget rule min(sims, upper - sum_n) and the moves equal the reference's."""
+    g = golden(f"mcts_game_{S}.npz")
+    sims, upper = int(g["sims"]), int(g["upper"])
+    eng = _engine(S, 1, sims, upper, training=False)
+    pv = omcts.table_pv_fn(S, int(g["salt"]))
+    for t in range(len(g["action"])):
+        eng.set_roots(g["boards"][t][None], _cells(g["last"][t][None], S))
+        assert int(eng.sims_left().cpu()[0]) == int(g["budget"][t])
+        eng.run_search(pv_fn=pv)
+        n, w, _, s = [x.cpu().numpy() for x in eng.root_stats()]
+        assert (n[0] == g["n"][t].reshape(-1)).all() and s[0] == g["sum_n"][t]
+        assert (w[0] == g["w"][t].reshape(-1)).all()
+        _, action = eng.finish_move()
+        assert int(action.cpu()[0]) == g["action"][t][0] * S + g["action"][t][1]
+    eng.close()
+
+
+def test_matches_oracle_on_many_roots_with_device_net(cuda_lib):
+    """N different mid-game roots searched in lock-step with the on-device fp32 net; the
+    oracle runs the same searches with the oracle net.  Visit counts agree exactly on
+    nearly every root (fp32 rounding of the two nets can flip a near-tie)."""
+    from alphafive_b200.net import DeviceNet, glorot_init
+    from oracle import net as onet
+    S, sims = 11, 64
+    g = golden("replay_sample.npz")
+    boards, last = g["boards"][:48], g["last_action"][:48]
+    w = glorot_init(S, 3)
+    net = DeviceNet(S, 48, w)
+    eng = _engine(S, 48, sims, sims + 100, training=False)
+    eng.set_roots(boards, _cells(last, S))
+    eng.run_search(net=net, check_every=4)
+    n = eng.root_stats()[0].cpu().numpy()
+    onet_ = onet.OracleNet(S, w)
+    same = 0
+    for j in range(48):
+        pl = omcts.OraclePlayer(omcts.SearchConfig(simulation_per_step=sims, upper_simulation_per_step=sims + 100),
+                                training=False, pv_fn=onet_.eval)
+        la = tuple(int(v) for v in last[j])
+        pl.get_action(boards[j], la if la[0] >= 0 else None)
+        same += int((pl.root_stats(boards[j])[0] == n[j]).all())
+        assert n[j].sum() == sims - 1
+    assert same >= 44, same
+
+
+def test_training_mode_distribution(cuda_lib):
+    """Forced-visit ladder and per-visit Dirichlet mixing: summary statistics against 64
+    seeded searches of the reference (tests/golden/mcts_train_11.npz)."""
+    g = golden("mcts_train_11.npz")
+    ref = g["n"]
+    S, sims, N = 11, int(g["sims"]), 256
+    eng = _engine(S, N, sims, sims + 100, training=True, seed=11)
+    eng.set_roots(np.zeros((N, S, S), np.int8), np.full(N, -1, np.int32))
+    eng.run_search(pv_fn=omcts.table_pv_fn(S, int(g["salt"])))
+    n = eng.root_stats()[0].cpu().numpy()
+    c = eng.counters()
+    assert n.min() >= 2 and (n.sum(1) == sims - 1).all()
+    assert abs(n.max(1).mean() - ref.max(1).mean()) < 0.6
+    assert np.abs(np.sort(n, 1).mean(0) - np.sort(ref, 1).mean(0))[:-2].max() < 0.3
+    depth = c["selects"] / c["sims"]
+    assert abs(depth - g["depth"].mean()) < 0.05, depth
+    assert len({r.tobytes() for r in n}) > N // 2            # independent Philox streams per game
+    eng.close()
+
+
+def test_forced_visit_picks_are_uniform(cuda_lib):
+    """Root, training: while unvisited children exist one is drawn uniformly (player.py:264-271)."""
+    S, N = 11, 4096
+    eng = _engine(S, N, 3, 103, training=True, seed=5)
+
+    def uniform_pv(x):
+        B = x.shape[0]
+        return np.full((B, S * S), 1.0 / (S * S), np.float32), np.zeros(B, np.float32)
+
+    eng.set_roots(np.zeros((N, S, S), np.int8), np.full(N, -1, np.int32))
+    eng.run_search(pv_fn=uniform_pv)
+    n = eng.root_stats()[0].cpu().numpy()
+    assert (n.sum(1) == 2).all() and n.max() == 1           # forced ladder: two distinct unvisited cells
+    freq = n.sum(0) / (2 * N)
+    assert abs(freq - 1 / 121).max() < 0.004                # uniform picks among the unvisited
+    eng.close()
+
+
+def test_self_play_records(cuda_lib):
+    """auto_play: whole games on the device (Player.run + gen_data): record invariants of
+    player.py:53-82 / main.py:86-93 / utils.py:286-296."""
+    from alphafive_b200.engine import parse_records
+    from alphafive_b200.net import DeviceNet
+    S, N, sims = 11, 64, 24
+    net = DeviceNet(S, N)
+    eng = _engine(S, N, sims, sims + 10, training=True, auto_play=True, seed=1)
+    prob = torch.empty((N, S * S), device="cuda")
+    value = torch.empty((N,), device="cuda")
+    eng.step()
+    recs, games = [], 0
+    for it in range(40000):
+        net.forward_raw(eng.planes_ptr, N, prob, value)
+        eng.step(prob, value)
+        if it % 500 == 499:
+            buf, g_ = eng.harvest()
+            recs += parse_records(buf, S)
+            games += g_
+            if games >= 40:
+                break
+    assert games >= 40
+    c = eng.counters()
+    assert c["overflows"] == 0 and c["records_dropped"] == 0 and c["games"] >= games
+    by_game = {}
+    for r in recs:
+        by_game.setdefault((r["game_id"], r["game_serial"]), []).append(r)
+    assert len(by_game) == games
+    lens = []
+    for key, plies in by_game.items():
+        plies.sort(key=lambda r: r["ply"])
+        L = plies[0]["game_len"]
+        lens.append(L)
+        assert [r["ply"] for r in plies] == list(range(L)) and 9 <= L <= 121
+        assert not plies[0]["board"].any() and plies[0]["last_action"] == -1
+        for t in range(L - 1):
+            a = plies[t + 1]["last_action"]
+            assert plies[t]["board"].reshape(-1)[a] == 0
+            assert (orules.play(plies[t]["board"], (a // S, a % S)) == plies[t + 1]["board"]).all()
+            assert orules.terminal_code(plies[t + 1]["board"]) == 0
+        for r in plies:
+            pol = r["policy"].reshape(-1)
+            assert abs(pol.sum() - 1) < 1e-4 and (pol[r["board"].reshape(-1) != 0] == 0).all()
+        final_moves = [orules.terminal(orules.play(plies[-1]["board"], a)) for a in orules.legal_actions(plies[-1]["board"])]
+        vals = np.array([r["value"] for r in plies])
+        if plies[0]["result"] == 0:
+            assert (vals == 0).all() and (True, 0.0) in final_moves
+        else:
+            assert vals[-1] == 1.0 and (vals[1:] == -vals[:-1]).all() and (True, -1.0) in final_moves
+            assert plies[0]["result"] == (1 if L % 2 == 1 else -1)
+        np.testing.assert_allclose([r["weight"] for r in plies], orules.ply_weights(L, 0.94), atol=1e-6)
+    assert np.mean(lens) > 12
+    eng.close()

@@ -1,0 +1,67 @@
+"""Device policy/value net vs the fp32 torch-CPU oracle: |dp|, |dv| <= 1e-4 (north star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import net as onet, rules as orules
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ckpt():
+    z = golden("ckpt6960.npz")
+    return {k.replace("__", "/"): z[k] for k in z.files}
+
+
+def _planes(boards, last):
+    return np.stack([orules.input_planes(b, tuple(la) if la[0] >= 0 else None) for b, la in zip(boards, last)])
+
+
+def _modes():
+    from alphafive_b200 import _lib
+    return [_lib.NET_FP32, _lib.NET_TC]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_trained_weights_parity(cuda_lib, mode):
+    from alphafive_b200.net import DeviceNet
+    g = golden("replay_sample.npz")
+    x = _planes(g["boards"], g["last_action"])
+    w = _ckpt()
+    want_p, want_v = onet.OracleNet(11, w).eval(x)
+    net = DeviceNet(11, 1024, w, mode=mode)
+    got_p, got_v = net.eval(x)
+    assert np.abs(got_p - want_p).max() <= TOL, np.abs(got_p - want_p).max()
+    assert np.abs(got_v - want_v).max() <= TOL, np.abs(got_v - want_v).max()
+    assert (got_p.argmax(1) == want_p.argmax(1)).mean() > 0.995
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("S", [11, 15])
+def test_random_init_parity(cuda_lib, S, mode):
+    from alphafive_b200.net import DeviceNet, glorot_init
+    rng = np.random.default_rng(S)
+    boards = np.stack([orules.random_board(rng, S) for _ in range(300)])
+    last = rng.integers(-1, S, size=(300, 2))
+    last[last[:, 0] < 0] = -1
+    x = _planes(boards, last)
+    w = glorot_init(S, seed=0)
+    ow = onet.glorot_weights(S, seed=0)
+    assert all(np.array_equal(w[k], ow[k]) for k in w)         # same "random-init" definition
+    want_p, want_v = onet.OracleNet(S, w).eval(x)
+    net = DeviceNet(S, 128, w, mode=mode)                      # 300 boards -> 3 chunks, one ragged
+    got_p, got_v = net.eval(x)
+    assert np.abs(got_p - want_p).max() <= TOL, np.abs(got_p - want_p).max()
+    assert np.abs(got_v - want_v).max() <= TOL, np.abs(got_v - want_v).max()
+    np.testing.assert_allclose(got_p.sum(1), 1.0, atol=1e-5)
+
+
+def test_eval_is_the_reference_pv_fn_seam(cuda_lib):
+    """ResNet.eval contract (network.py:90-97): f32 [B,3,S,S] -> (f32 [B,S*S], f32 [B])."""
+    from alphafive_b200.net import DeviceNet
+    net = DeviceNet(11, 8)
+    x = np.zeros((1, 3, 11, 11), np.float32)
+    p, v = net.eval(x)
+    assert p.shape == (1, 121) and v.shape == (1,) and p.dtype == np.float32 and v.dtype == np.float32
