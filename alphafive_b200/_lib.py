@@ -56,6 +56,8 @@ _SIGS = {
     "a5_engine_reset": (_I, [_P, _P]),
     "a5_engine_set_roots": (_I, [_P, _P, _P, _P, _P, _P]),
     "a5_engine_step": (_I, [_P, _P, _P, _P]),
+    "a5_engine_set_mode": (_I, [_P, _I, _I]),
+    "a5_engine_set_budget": (_I, [_P, _I, _I]),
     "a5_engine_planes": (_P, [_P]),
     "a5_engine_need_eval": (_P, [_P]),
     "a5_engine_sims_left": (_P, [_P]),

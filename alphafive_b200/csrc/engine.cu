@@ -997,6 +997,20 @@ int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void
   return A5_OK;
 }
 
+int a5_engine_set_mode(a5_engine* e, int training, int random_a) {
+  A5_ARG(e);
+  e->p.training = training != 0;
+  e->p.random_a = random_a != 0;
+  return A5_OK;
+}
+
+int a5_engine_set_budget(a5_engine* e, int sims, int upper_sims) {
+  A5_ARG(e && sims > 0 && upper_sims >= 0);
+  e->p.sims = sims;
+  e->p.upper = upper_sims;
+  return A5_OK;
+}
+
 int8_t* a5_engine_planes(a5_engine* e) { return e ? e->p.planes : nullptr; }
 uint8_t* a5_engine_need_eval(a5_engine* e) { return e ? e->p.need_eval : nullptr; }
 int32_t* a5_engine_sims_left(a5_engine* e) { return e ? e->p.sims_left : nullptr; }

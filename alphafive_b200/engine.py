@@ -73,6 +73,12 @@ class SearchEngine:
         check(self.lib.a5_engine_set_roots(self.handle, ptr(boards), ptr(last_t), ptr(act_t), ptr(clr_t), stream_ptr()))
         self._first = True
 
+    def set_mode(self, training: bool, random_a: bool = False):
+        check(self.lib.a5_engine_set_mode(self.handle, int(training), int(random_a)))
+
+    def set_budget(self, sims: int, upper: int):
+        check(self.lib.a5_engine_set_budget(self.handle, int(sims), int(upper)))
+
     def step(self, prob=None, value=None):
         if self._first:
             prob = value = None

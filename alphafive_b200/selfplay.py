@@ -1,0 +1,147 @@
+"""Lock-step self-play drivers.
+
+``SelfPlay``       -- the data-generating loop of the reference (main.py:82-94 ->
+                      Player.run, player.py:53-82) for N games at once, entirely on the
+                      device: games are played, recorded and restarted by the tree kernel;
+                      the host only launches passes and harvests finished-game records.
+``BatchedPlayer``  -- N ``Player`` objects behind one call with HOST buffers:
+                      ``get_actions(boards, last_actions) -> (policies, actions)`` is
+                      ``Player.get_action`` (player.py:128-147) batched; host<->device
+                      copies go through pinned memory.  This is the reference-facing API
+                      the end-to-end number of bench.py is measured through.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import rules
+from .engine import SearchEngine, make_config, parse_records
+from .net import DeviceNet
+
+
+class SelfPlay:
+    def __init__(self, cfg=None, n_games=4096, net: DeviceNet | None = None, training=True, seed=0,
+                 game_id_base=0, use_graph=True, **cfg_kw):
+        self.config = make_config(cfg, n_games=n_games, training=training, auto_play=True, seed=seed,
+                                  game_id_base=game_id_base, **cfg_kw)
+        self.engine = SearchEngine(self.config)
+        self.N, self.S = n_games, self.config.board_size
+        self.net = net if net is not None else DeviceNet(self.S, n_games)
+        dev = self.engine.device
+        self.prob = torch.zeros((n_games, self.S * self.S), dtype=torch.float32, device=dev)
+        self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
+        self.record_buf = torch.empty((self.config.record_capacity or n_games * self.S * self.S,
+                                       self.engine.record_stride), dtype=torch.uint8, device=dev)
+        self.use_graph = use_graph
+        self._graph = None
+        self._started = False
+        self.passes = 0
+
+    # one pass = network forward over all N pending leaves + one tree-kernel pass
+    def _pass(self):
+        self.net.forward_raw(self.engine.planes_ptr, self.N, self.prob, self.value)
+        self.engine.step(self.prob, self.value)
+
+    def start(self):
+        if not self._started:
+            self.engine.step()              # first descent: every game reaches its (unseen) root
+            self._started = True
+            if self.use_graph:
+                # warm up on a side stream, then capture one pass
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._pass()
+                torch.cuda.current_stream().wait_stream(s)
+                self.passes += 1
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):     # capture only: nothing executes here
+                    self._pass()
+
+    def run_passes(self, k: int):
+        self.start()
+        if self._graph is not None:
+            for _ in range(k):
+                self._graph.replay()
+        else:
+            for _ in range(k):
+                self._pass()
+        self.passes += k
+
+    def harvest(self):
+        """(records uint8 [count, stride] on the device, games finished since last call)."""
+        return self.engine.harvest(self.record_buf)
+
+    def harvest_games(self):
+        """Finished games as the reference's replay tuples (player.py:77-82):
+        list of (record list, result) like main.py:94's q.put((game_record, result))."""
+        buf, _ = self.harvest()
+        return records_to_games(parse_records(buf, self.S), self.S)
+
+    def counters(self):
+        return self.engine.counters()
+
+
+def records_to_games(recs, S):
+    from .genData.player import board_to_state
+    by = {}
+    for r in recs:
+        by.setdefault((r["game_id"], r["game_serial"]), []).append(r)
+    games = []
+    for key in sorted(by):
+        plies = sorted(by[key], key=lambda r: r["ply"])
+        rec = []
+        for r in plies:
+            la = None if r["last_action"] < 0 else (r["last_action"] // S, r["last_action"] % S)
+            rec.append((board_to_state(r["board"]), r["policy"], la, float(r["value"]), np.float32(r["weight"])))
+        games.append((rec, int(plies[0]["result"])))
+    return games
+
+
+class BatchedPlayer:
+    """N reference ``Player`` objects in lock-step, host buffers in and out."""
+
+    def __init__(self, cfg=None, n_players=1, net: DeviceNet | None = None, training=True, random_a=False,
+                 seed=0, game_id_base=0, check_every=16, **cfg_kw):
+        self.config = make_config(cfg, n_games=n_players, training=training, random_a=random_a,
+                                  auto_play=False, seed=seed, game_id_base=game_id_base, **cfg_kw)
+        self.engine = SearchEngine(self.config)
+        self.N, self.S = n_players, self.config.board_size
+        self.C = self.S * self.S
+        self.net = net if net is not None else DeviceNet(self.S, n_players)
+        self.check_every = check_every
+        dev = self.engine.device
+        N, S, C = self.N, self.S, self.C
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+        self.h_boards, self.h_last = pin(N, S, S, dtype=torch.int8), pin(N, dtype=torch.int32)
+        self.h_policy, self.h_action = pin(N, C, dtype=torch.float32), pin(N, dtype=torch.int32)
+        self.h_next, self.h_codes = pin(N, S, S, dtype=torch.int8), pin(N, dtype=torch.int8)
+        self.d_boards = torch.empty((N, S, S), dtype=torch.int8, device=dev)
+        self.d_last = torch.empty((N,), dtype=torch.int32, device=dev)
+        self.h2d_bytes = N * C + 4 * N
+        self.d2h_bytes = N * C * 4 + 4 * N + N * C + N
+
+    def get_actions(self, boards, last, active=None, clear=None, advance=False):
+        """boards int8[N,S,S] / last int32[N] host arrays -> (policy f32[N,S,S], action int32[N])
+        host arrays.  With ``advance`` the played positions and their terminal codes are
+        returned as well (utils.step + utils.is_game_over on the device)."""
+        self.h_boards.copy_(torch.as_tensor(boards, dtype=torch.int8).reshape(self.N, self.S, self.S))
+        self.h_last.copy_(torch.as_tensor(last, dtype=torch.int32))
+        self.d_boards.copy_(self.h_boards, non_blocking=True)
+        self.d_last.copy_(self.h_last, non_blocking=True)
+        self.engine.set_roots(self.d_boards, self.d_last, active, clear)
+        self.engine.run_search(net=self.net, check_every=self.check_every)
+        policy, action = self.engine.finish_move()
+        self.h_policy.copy_(policy, non_blocking=True)
+        self.h_action.copy_(action, non_blocking=True)
+        if advance:
+            nxt = rules.step(self.d_boards, action.clamp(min=0))
+            codes = rules.terminal(nxt, self.config.goal)
+            self.h_next.copy_(nxt, non_blocking=True)
+            self.h_codes.copy_(codes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        pol = self.h_policy.numpy().reshape(self.N, self.S, self.S)
+        if advance:
+            return pol, self.h_action.numpy(), self.h_next.numpy(), self.h_codes.numpy()
+        return pol, self.h_action.numpy()

@@ -121,6 +121,13 @@ int a5_engine_set_roots(a5_engine* e, const int8_t* d_boards, const int32_t* d_l
  * prob/value on the very first pass after create/reset/set_roots. */
 int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void* stream);
 
+/* Per-call arguments of the reference API that are engine state here: the `training`
+ * attribute / `random_a` argument of get_action (player.py:24,128) and the lazily read
+ * config.simulation_per_step / upper_simulation_per_step (choose_best_player.py:25 mutates
+ * them at run time).  Take effect from the next kernel launch. */
+int a5_engine_set_mode(a5_engine* e, int training, int random_a);
+int a5_engine_set_budget(a5_engine* e, int sims, int upper_sims);
+
 int8_t*  a5_engine_planes(a5_engine* e);      /* int8 [N][3][S*S]   utils.py:256-272 */
 uint8_t* a5_engine_need_eval(a5_engine* e);   /* uint8[N]                            */
 int32_t* a5_engine_sims_left(a5_engine* e);   /* int32[N] remaining budget           */
