@@ -28,6 +28,7 @@ int fp32_alloc(a5_net* net);
 void fp32_free(a5_net* net);
 int fp32_set_weights(a5_net* net, const float* const* t, cudaStream_t st);
 int fp32_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st);
+int fp32_heads(a5_net* net, int n, float* prob, float* value, cudaStream_t st);
 
 int tc_alloc(a5_net* net);
 void tc_free(a5_net* net);

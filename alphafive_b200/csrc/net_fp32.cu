@@ -386,12 +386,22 @@ int fp32_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* v
     a.mode = 0; a.act = 1;
     rc = L.cout == 32 ? launch_gemm<32>(a, st) : launch_gemm<64>(a, st);
     if (rc) return rc;
-    if (l == 6) {   // value head reads block3's output
-      k_value_head<<<n, 128, 0, st>>>(net->act[B3O], net->vconv_w, net->vconv_b, net->vfc1_w, net->vfc1_b,
-                                     net->vfc2_w, net->vfc2_b, value, S, ps.pitch, ps.per_board, ps.guard);
-      A5_CUDA(cudaGetLastError());
-    }
   }
+  return fp32_heads(net, n, prob, value, st);
+}
+
+// Heads on the fp32 [row][32] outputs of block3 (value) and block5 (policy); shared by both
+// compute paths (the tensor-core epilogue of those two layers also emits fp32 rows).
+int fp32_heads(a5_net* net, int n, float* prob, float* value, cudaStream_t st) {
+  PosSpace ps(net->S);
+  const int S = net->S, C = net->C;
+  int rc;
+  k_value_head<<<n, 128, 0, st>>>(net->act[B3O], net->vconv_w, net->vconv_b, net->vfc1_w, net->vfc1_b,
+                                 net->vfc2_w, net->vfc2_b, value, S, ps.pitch, ps.per_board, ps.guard);
+  A5_CUDA(cudaGetLastError());
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.S = S; a.pitch = ps.pitch; a.per_board = ps.per_board; a.guard = ps.guard; a.C = C;
   // policy head: 1x1 conv 32->16 + ELU into the c-major flat layout, dense, softmax
   a.nseg = 1; a.seg[0] = Seg{net->act[B5O], 32, 0, 32};
   a.W = net->w[11]; a.ldw = 64; a.bias = net->bias[11];
