@@ -273,9 +273,9 @@ def run_ours(a):
     if world > 1:
         em = e2e.clone(); dist.all_reduce(em, op=dist.ReduceOp.MAX)
         es = e2e.clone(); dist.all_reduce(es, op=dist.ReduceOp.SUM)
-        e2e_val = es[1].item() / em[0].item()
+        e2e_val = es[1].item() / em[0].item() if em[0].item() > 0 else None
     else:
-        e2e_val = e2e_moves / e2e_t
+        e2e_val = e2e_moves / e2e_t if e2e_t > 0 else None
 
     if rank == 0:
         pk = peaks()
