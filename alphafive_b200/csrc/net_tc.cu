@@ -22,23 +22,30 @@
 // stage (4*Cout <= 512 TMEM columns).  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer,
 // 2..5 = epilogue (TMEM -> registers -> bias/ELU/split -> coalesced 16-byte stores).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "net.cuh"
 
 namespace a5 {
 
-constexpr int TC_T = 4;                 // M tiles per group
-constexpr int TC_ROWS = TC_T * 128;     // positions per group
 constexpr int TC_HALO = 24;             // >= pitch + 1 for S <= 15, multiple of 8
-constexpr int TC_SROWS = TC_ROWS + 2 * TC_HALO;   // staged positions per slab plane (560)
-constexpr int TC_PLANE = TC_SROWS * 16;           // bytes per (kchunk) plane in smem (8960)
 constexpr int TC_KS = 32;               // channels per slab
-constexpr int TC_SLAB = 2 * (TC_KS / 8) * TC_PLANE;   // hi+lo, 4 kchunks: 71,680 bytes
-constexpr int TC_WSTAGES = 4;
 constexpr int TC_WSTAGE_MAX = 2 * (TC_KS / 8) * 128 * 16;   // 16 KB (Cout = 128)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;         // two per TMEM lane quadrant
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr float ACT_SCALE = 16.0f;      // 2^4
 constexpr float W_SCALE = 1024.0f;      // 2^10
 constexpr float OUT_SCALE = 1.0f / (16.0f * 1024.0f);
+
+// T = M tiles (of 128 positions) per group; a group shares every weight stage.
+template <int T>
+struct TCfg {
+  static constexpr int ROWS = T * 128;                 // positions per group
+  static constexpr int SROWS = ROWS + 2 * TC_HALO;     // staged positions per slab plane
+  static constexpr int PLANE = SROWS * 16;             // bytes per (kchunk) plane in smem
+  static constexpr int SLAB = 2 * (TC_KS / 8) * PLANE; // hi+lo, 4 kchunks
+  static constexpr int WSTAGES = T >= 4 ? 4 : 8;
+  static constexpr int SMEM = 2 * SLAB + WSTAGES * TC_WSTAGE_MAX + 128 * 4 + 256 + 128;
+};
 
 struct TCLayer {
   const __half* src; int src_ch;
@@ -123,31 +130,42 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
 }
 
 struct __align__(8) TCBarriers {
-  uint64_t a_full[2], a_empty[2], w_full[TC_WSTAGES], w_empty[TC_WSTAGES], t_full[2], t_empty[2];
+  uint64_t a_full[2], a_empty[2], w_full[8], w_empty[8], t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
+static_assert(sizeof(TCBarriers) <= 256, "barrier block outgrew its smem reservation");
+
+// exp(x) - 1 for x <= 0 through ex2.approx (abs error ~1e-7: below the fp32 rounding of the
+// O(1) activations it feeds); expm1f costs ~10x the issue slots in the epilogue.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ------------------------------------------------------------------ the conv kernel
+template <int T>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant__ TCLayer L) {
+  using Cfg = TCfg<T>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* a_buf = smem;                                   // 2 slabs
-  uint8_t* w_buf = smem + 2 * TC_SLAB;                     // TC_WSTAGES stages
-  float* s_bias = (float*)(w_buf + TC_WSTAGES * TC_WSTAGE_MAX);
+  uint8_t* w_buf = smem + 2 * Cfg::SLAB;                   // WSTAGES stages
+  float* s_bias = (float*)(w_buf + Cfg::WSTAGES * TC_WSTAGE_MAX);
   TCBarriers* B = (TCBarriers*)(s_bias + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cout = L.cout;
-  const int nbuf = (TC_T * cout <= 256) ? 2 : 1;           // TMEM accumulator buffers
+  const int nbuf = (T * cout <= 256) ? 2 : 1;              // TMEM accumulator buffers
   const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
   const int nslabs = main_slabs + res_slabs;
   const uint32_t stage_bytes = 2u * (TC_KS / 8) * cout * 16u;
 
-  if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x];
+  if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&B->a_full[i], 1); mbar_init(&B->a_empty[i], 1); }
-    for (int i = 0; i < TC_WSTAGES; ++i) { mbar_init(&B->w_full[i], 1); mbar_init(&B->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], 4); }
+    for (int i = 0; i < Cfg::WSTAGES; ++i) { mbar_init(&B->w_full[i], 1); mbar_init(&B->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
     if (lane == 0) {
       int ab = 0, aph = 0, ws = 0, wph = 0;
       for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-        const long long r0 = L.row0 + (long long)g * TC_ROWS - TC_HALO;
+        const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
         const __half* wsrc = L.wpk;
         for (int s = 0; s < nslabs; ++s) {
           const bool is_res = s >= main_slabs;
@@ -172,14 +190,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
           const int xch = is_res ? L.res_ch : L.src_ch;
           const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
           mbar_wait(&B->a_empty[ab], aph ^ 1);
-          mbar_expect_tx(&B->a_full[ab], TC_SLAB);
-          uint8_t* dst = a_buf + ab * TC_SLAB;
+          mbar_expect_tx(&B->a_full[ab], Cfg::SLAB);
+          uint8_t* dst = a_buf + ab * Cfg::SLAB;
 #pragma unroll
           for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
             for (int j = 0; j < TC_KS / 8; ++j) {
               const __half* p = X + ((long long)(hl * (xch / 8) + kc0 + j) * L.plane_rows + r0) * 8;
-              bulk_g2s(dst + (hl * (TC_KS / 8) + j) * TC_PLANE, p, TC_PLANE, &B->a_full[ab]);
+              bulk_g2s(dst + (hl * (TC_KS / 8) + j) * Cfg::PLANE, p, Cfg::PLANE, &B->a_full[ab]);
             }
           if (++ab == 2) { ab = 0; aph ^= 1; }
           const int ntap = is_res ? 1 : L.ntaps;
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
             mbar_expect_tx(&B->w_full[ws], stage_bytes);
             bulk_g2s(w_buf + ws * TC_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
             wsrc += stage_bytes / 2;
-            if (++ws == TC_WSTAGES) { ws = 0; wph ^= 1; }
+            if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
           }
         }
       }
@@ -203,34 +221,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
       for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
         mbar_wait(&B->t_empty[tb], tph ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem + (uint32_t)(tb * TC_T * cout);
+        const uint32_t d0 = tmem + (uint32_t)(tb * T * cout);
         for (int s = 0; s < nslabs; ++s) {
           const bool is_res = s >= main_slabs;
           const int ntap = is_res ? 1 : L.ntaps;
           mbar_wait(&B->a_full[ab], aph);
           tc_fence_after();
-          const uint32_t a_slab = a_base + ab * TC_SLAB;
+          const uint32_t a_slab = a_base + ab * Cfg::SLAB;
           for (int t = 0; t < ntap; ++t) {
             const int shift = is_res ? 0 : L.shifts[t];
             mbar_wait(&B->w_full[ws], wph);
             tc_fence_after();
             const uint32_t w_st = w_base + ws * TC_WSTAGE_MAX;
 #pragma unroll
-            for (int m = 0; m < TC_T; ++m) {
+            for (int m = 0; m < T; ++m) {
               const uint32_t a_row = a_slab + (uint32_t)(TC_HALO + m * 128 + shift) * 16u;
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass) {       // hi*hi, lo*hi, hi*lo
                 const int ah = pass == 1, wh = pass == 2;
 #pragma unroll
                 for (int k = 0; k < TC_KS / 16; ++k) {
-                  uint64_t ad = smem_desc(a_row + (uint32_t)((ah * (TC_KS / 8) + 2 * k) * TC_PLANE), TC_PLANE, 128);
+                  uint64_t ad = smem_desc(a_row + (uint32_t)((ah * (TC_KS / 8) + 2 * k) * Cfg::PLANE), Cfg::PLANE, 128);
                   uint64_t bd = smem_desc(w_st + (uint32_t)(wh * (TC_KS / 8) + 2 * k) * w_lbo, w_lbo, 128);
                   tc_mma(d0 + (uint32_t)(m * cout), ad, bd, idesc, (s | t | pass | k) != 0);
                 }
               }
             }
             tc_commit(&B->w_empty[ws]);                    // stage reusable once these MMAs retire
-            if (++ws == TC_WSTAGES) { ws = 0; wph ^= 1; }
+            if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
           }
           tc_commit(&B->a_empty[ab]);
           if (++ab == 2) { ab = 0; aph ^= 1; }
@@ -241,49 +259,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
     }
   } else {
     // ===================== epilogue: TMEM -> bias / ELU / hi-lo split -> HBM =====================
-    const int quad = warp & 3;                              // TMEM lane quadrant this warp may read
+    // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); they
+    // take alternate M tiles.  All arithmetic is on values pre-scaled by ACT_SCALE.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     int tb = 0, tph = 0;
     const long long row_end = L.row0 + L.nrows;
+    constexpr float K_ACC = OUT_SCALE * ACT_SCALE;          // accumulator -> scaled activation
+    constexpr float K_L2E = 1.4426950408889634f / ACT_SCALE;
     for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
       mbar_wait(&B->t_full[tb], tph);
       tc_fence_after();
-      for (int m = 0; m < TC_T; ++m) {
-        const long long row = L.row0 + (long long)g * TC_ROWS + m * 128 + quad * 32 + lane;
+      for (int m = half; m < T; m += 2) {
+        const long long row = L.row0 + (long long)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
         const long long q = row - L.row0;
         const int within = (int)(q % L.per_board);
         const int rr = within / L.pitch, cc = within % L.pitch;
         const bool real = row < row_end && rr < L.S && cc < L.S;
         for (int c0 = 0; c0 < cout; c0 += 32) {
           uint32_t v[32];
-          tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * TC_T * cout + m * cout + c0), v);
+          tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cout + m * cout + c0), v);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), OUT_SCALE, s_bias[c0 + j]);
-            f[j] = real ? elu(x) : 0.0f;
+          for (int e = 0; e < 8; ++e) {
+            const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+              const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+              f[4 * e + j] = x > 0.0f ? x : neg;
+            }
           }
           if (L.out) {
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
-              __half2 hi[4], lo[4];
+              uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float x0 = f[kc * 8 + 2 * e] * ACT_SCALE, x1 = f[kc * 8 + 2 * e + 1] * ACT_SCALE;
-                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                hi[e] = __halves2half2(h0, h1);
-                lo[e] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+                const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[e] = real ? *(const uint32_t*)&h : 0u;
+                lo[e] = real ? *(const uint32_t*)&l : 0u;
               }
               const long long chunk = (c0 >> 3) + kc;
               __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
               __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
-              *(uint4*)ph = *(uint4*)hi;
-              *(uint4*)pl = *(uint4*)lo;
+              *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
           if (L.out_f32 && row < row_end) {
+            constexpr float inv = 1.0f / ACT_SCALE;
             float4* po = (float4*)(L.out_f32 + row * cout + c0);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) po[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+            for (int e = 0; e < 8; ++e)
+              po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
       }
@@ -413,7 +447,7 @@ struct a5_tc_state {
   __half* act[11] = {};
   __half* wpk[11] = {};
   long long plane_rows = 0;
-  int smem_bytes = 0;
+  int t128 = 2;
   int num_sms = 0;
 };
 
@@ -422,7 +456,7 @@ namespace a5 {
 static long long tc_plane_rows(const a5_net* net) {
   PosSpace ps(net->S);
   long long valid = (long long)net->max_batch * ps.per_board;
-  long long padded = (valid + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+  long long padded = (valid + 511) / 512 * 512;          // whole groups for every T
   return ps.guard + padded + ps.guard + TC_HALO;
 }
 
@@ -440,8 +474,10 @@ int tc_alloc(a5_net* net) {
     size_t stages = (size_t)(L.cin / TC_KS) * 9 + (L.res_src >= 0 ? L.res_cin / TC_KS : 0);
     A5_CUDA(cudaMalloc(&tc->wpk[l], stages * 2 * TC_KS * L.cout * sizeof(__half)));
   }
-  tc->smem_bytes = 2 * TC_SLAB + TC_WSTAGES * TC_WSTAGE_MAX + 128 * 4 + (int)sizeof(TCBarriers) + 128;
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, tc->smem_bytes));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
+  const char* t128 = getenv("A5_TC_T128");              // tuning knob: M tiles per group for Cout = 128
+  tc->t128 = (t128 && atoi(t128) == 4) ? 4 : 2;
   int dev = 0;
   A5_CUDA(cudaGetDevice(&dev));
   A5_CUDA(cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -469,15 +505,20 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
   return A5_OK;
 }
 
+// profiling hook (a5__debug_layer_times): when set, an event is recorded after every launch group
+static cudaEvent_t* g_tc_events = nullptr;
+#define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
+
 // heads + biases come from the fp32 path's packed copies (fp32_set_weights runs first)
 int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st) {
   a5_tc_state* tc = net->tc;
   PosSpace ps(net->S);
+  TC_MARK(0);
   k_tc_conv1<<<n, 128, 0, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
                                ps.per_board, ps.guard);
   A5_CUDA(cudaGetLastError());
+  TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
-  const int ngroups = (int)((nrows + TC_ROWS - 1) / TC_ROWS);
   for (int l = 1; l <= 10; ++l) {
     const TcLayerDef& D = kTcLayers[l];
     TCLayer L;
@@ -492,19 +533,50 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
+    const int T = (D.cout == 128) ? tc->t128 : 4;
+    const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows; L.ngroups = ngroups;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
     int grid = ngroups < tc->num_sms ? ngroups : tc->num_sms;
-    k_tc_conv<<<grid, TC_THREADS, tc->smem_bytes, st>>>(L);
+    if (T == 4) k_tc_conv<4><<<grid, TC_THREADS, TCfg<4>::SMEM, st>>>(L);
+    else k_tc_conv<2><<<grid, TC_THREADS, TCfg<2>::SMEM, st>>>(L);
     A5_CUDA(cudaGetLastError());
+    TC_MARK(1 + l);
   }
-  return fp32_heads(net, n, prob, value, st);
+  int rc = fp32_heads(net, n, prob, value, st);
+  TC_MARK(12);
+  return rc;
 }
 
 }  // namespace a5
 
 extern "C" {
 int a5_net_tc_available(void) { return 1; }
+
+// internal tooling (not part of alphafive.h): average milliseconds of each launch group of the
+// tensor-core forward over `reps` runs: h_ms[0] conv1, h_ms[1..10] block convs, h_ms[11] heads.
+int a5__debug_layer_times(a5_net* net, const int8_t* d_planes, int n, int reps, float* d_prob, float* d_value,
+                          float* h_ms, void* stream) {
+  A5_ARG(net && d_planes && h_ms && reps > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev[13];
+  for (int i = 0; i < 13; ++i) A5_CUDA(cudaEventCreate(&ev[i]));
+  for (int i = 0; i < 12; ++i) h_ms[i] = 0.0f;
+  for (int r = 0; r < reps; ++r) {
+    g_tc_events = ev;
+    int rc = tc_forward(net, d_planes, n, d_prob, d_value, st);
+    g_tc_events = nullptr;
+    if (rc) return rc;
+    A5_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 12; ++i) {
+      float ms = 0.0f;
+      A5_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      h_ms[i] += ms / reps;
+    }
+  }
+  for (int i = 0; i < 13; ++i) cudaEventDestroy(ev[i]);
+  return A5_OK;
+}
 
 // internal tooling (not part of alphafive.h): activation `idx` of the last forward of `mode`
 // as fp32 [rows][channels] with rows = n * (S+1)^2, for layer-by-layer parity debugging.
