@@ -30,7 +30,7 @@ namespace a5 {
 constexpr int TC_HALO = 24;             // >= pitch + 1 for S <= 15, multiple of 8
 constexpr int TC_KS = 32;               // channels per slab
 constexpr int TC_WSTAGE_MAX = 2 * (TC_KS / 8) * 128 * 16;   // 16 KB (Cout = 128)
-constexpr int TC_EPI_WARPS = 8;         // two per TMEM lane quadrant
+constexpr int TC_EPI_WARPS = 16;        // four per TMEM lane quadrant
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr float ACT_SCALE = 16.0f;      // 2^4
 constexpr float W_SCALE = 1024.0f;      // 2^10
@@ -55,6 +55,8 @@ struct TCLayer {
   __half* out;
   float* out_f32;
   int cout, ntaps;
+  int fold;                      // 1: hi*[Whi|Wlo] as one N = 2*cout MMA (cout <= 64)
+  unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
   int shifts[9];
   long long plane_rows;          // rows per channel-chunk plane in HBM (incl. guards)
   long long row0;                // first valid row (guard)
@@ -87,6 +89,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();      // a lost arrival must fail loudly, not hang the GPU
   }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -117,6 +128,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start >> 4 | [16,30) leading-dim byte offset >> 4 (K-adjacent core matrices)
 //   [32,46) stride byte offset >> 4 (8-row groups) | [46,48) version = 1 | [61,64) layout = 0
@@ -144,6 +174,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int role, int& n) {
+  if (dbg && blockIdx.x == 0 && n < 256) dbg[role * 256 + n++] = clock64();
+}
+
 // ------------------------------------------------------------------ the conv kernel
 template <int T>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant__ TCLayer L) {
@@ -156,7 +190,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cout = L.cout;
-  const int nbuf = (T * cout <= 256) ? 2 : 1;              // TMEM accumulator buffers
+  const int cpt = L.fold ? 2 * cout : cout;                // TMEM columns per M tile
+  const int nbuf = (T * cpt <= 256) ? 2 : 1;               // TMEM accumulator buffers
   const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
   const int nslabs = main_slabs + res_slabs;
   const uint32_t stage_bytes = 2u * (TC_KS / 8) * cout * 16u;
@@ -179,17 +214,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
 
   if (warp == 0) {
     // ===================== producer: bulk copies HBM -> SMEM =====================
-    if (lane == 0) {
-      int ab = 0, aph = 0, ws = 0, wph = 0;
-      for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-        const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
-        const __half* wsrc = L.wpk;
-        for (int s = 0; s < nslabs; ++s) {
-          const bool is_res = s >= main_slabs;
-          const __half* X = is_res ? L.res : L.src;
-          const int xch = is_res ? L.res_ch : L.src_ch;
-          const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
-          mbar_wait(&B->a_empty[ab], aph ^ 1);
+    // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
+    int ab = 0, aph = 0, ws = 0, wph = 0, dn = 0;
+    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
+      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
+      const __half* wsrc = L.wpk;
+      for (int s = 0; s < nslabs; ++s) {
+        const bool is_res = s >= main_slabs;
+        const __half* X = is_res ? L.res : L.src;
+        const int xch = is_res ? L.res_ch : L.src_ch;
+        const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
+        mbar_wait(&B->a_empty[ab], aph ^ 1);
+        if (lane == 0) dbg_mark(L.dbg, 0, dn);             // slab load issued
+        if (elect_one()) {
           mbar_expect_tx(&B->a_full[ab], Cfg::SLAB);
           uint8_t* dst = a_buf + ab * Cfg::SLAB;
 #pragma unroll
@@ -199,130 +236,190 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
               const __half* p = X + ((long long)(hl * (xch / 8) + kc0 + j) * L.plane_rows + r0) * 8;
               bulk_g2s(dst + (hl * (TC_KS / 8) + j) * Cfg::PLANE, p, Cfg::PLANE, &B->a_full[ab]);
             }
-          if (++ab == 2) { ab = 0; aph ^= 1; }
-          const int ntap = is_res ? 1 : L.ntaps;
-          for (int t = 0; t < ntap; ++t) {
-            mbar_wait(&B->w_empty[ws], wph ^ 1);
+        }
+        __syncwarp();
+        if (++ab == 2) { ab = 0; aph ^= 1; }
+        const int ntap = is_res ? 1 : L.ntaps;
+        for (int t = 0; t < ntap; ++t) {
+          mbar_wait(&B->w_empty[ws], wph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&B->w_full[ws], stage_bytes);
             bulk_g2s(w_buf + ws * TC_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
-            wsrc += stage_bytes / 2;
-            if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
           }
+          __syncwarp();
+          wsrc += stage_bytes / 2;
+          if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: one thread drives the tensor core =====================
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(128, cout);
-      const uint32_t a_base = smem_u32(a_buf), w_base = smem_u32(w_buf);
-      const uint32_t w_lbo = (uint32_t)cout * 16u;
-      int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0;
-      for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-        mbar_wait(&B->t_empty[tb], tph ^ 1);
+    // ===================== MMA issuer =====================
+    // Warp-uniform control flow (descriptor arithmetic stays in uniform registers); the
+    // tcgen05.mma / commit instructions themselves are issued by one elected lane.  The
+    // taps are unrolled with their shifts in registers so nothing but the barrier wait sits
+    // between the MMAs of consecutive stages.
+    const uint32_t idesc = instr_desc(128, cout), idesc2 = instr_desc(128, 2 * cout);
+    const uint32_t w_lbo = 2u * (uint32_t)cout * 16u;       // stage layout [kchunk][hi|lo][cout][8]
+    const bool fold = L.fold != 0;
+    // descriptor deltas (the start-address field counts 16-byte units)
+    constexpr uint64_t A_TILE = 128u * 16u / 16u;            // next M tile
+    constexpr uint64_t A_K16 = 2u * Cfg::PLANE / 16u;        // next 16 channels
+    constexpr uint64_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;  // hi -> lo planes
+    const uint64_t w_k16 = (uint64_t)(2u * w_lbo / 16u);
+    const uint64_t w_lo16 = (uint64_t)(cout * 16u / 16u);
+    const uint64_t ad_base = smem_desc(smem_u32(a_buf) + (uint32_t)TC_HALO * 16u, Cfg::PLANE, 128);
+    const uint64_t bd_base = smem_desc(smem_u32(w_buf), w_lbo, 128);
+    int sh[9];                                               // tap shifts, in rows (= 16-byte units)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
+    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0, dn = 0, dn3 = 0;
+    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: waiting for TMEM
+      mbar_wait(&B->t_empty[tb], tph ^ 1);
+      tc_fence_after();
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: TMEM free
+      const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt);
+      for (int s = 0; s < nslabs; ++s) {
+        const bool is_res = s >= main_slabs;
+        const int ntap = is_res ? 1 : L.ntaps;
+        mbar_wait(&B->a_full[ab], aph);
         tc_fence_after();
-        const uint32_t d0 = tmem + (uint32_t)(tb * T * cout);
-        for (int s = 0; s < nslabs; ++s) {
-          const bool is_res = s >= main_slabs;
-          const int ntap = is_res ? 1 : L.ntaps;
-          mbar_wait(&B->a_full[ab], aph);
-          tc_fence_after();
-          const uint32_t a_slab = a_base + ab * Cfg::SLAB;
-          for (int t = 0; t < ntap; ++t) {
-            const int shift = is_res ? 0 : L.shifts[t];
+        if (lane == 0) dbg_mark(L.dbg, 1, dn);             // slab landed
+        const uint64_t ad_slab = ad_base + (uint64_t)(ab * (Cfg::SLAB / 16));
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < ntap) {
+            if (lane == 0) dbg_mark(L.dbg, 3, dn3);        // stage: waiting for weights
             mbar_wait(&B->w_full[ws], wph);
             tc_fence_after();
-            const uint32_t w_st = w_base + ws * TC_WSTAGE_MAX;
+            if (lane == 0) dbg_mark(L.dbg, 3, dn3);        // stage: weights landed
+            const uint64_t ad0 = ad_slab + (uint64_t)(int64_t)(is_res ? 0 : sh[t]);
+            const uint64_t bd0 = bd_base + (uint64_t)(ws * (TC_WSTAGE_MAX / 16));
+            const uint32_t first = (uint32_t)(s | t);
+            const bool last_tap = t == ntap - 1;
+            if (elect_one()) {
+              if (fold) {
+                // a_hi * [w_hi | w_lo] -> columns [0, 2 cout); a_lo * w_hi accumulates into [0, cout)
 #pragma unroll
-            for (int m = 0; m < T; ++m) {
-              const uint32_t a_row = a_slab + (uint32_t)(TC_HALO + m * 128 + shift) * 16u;
+                for (int m = 0; m < T; ++m) {
 #pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {       // hi*hi, lo*hi, hi*lo
-                const int ah = pass == 1, wh = pass == 2;
+                  for (int k = 0; k < TC_KS / 16; ++k)
+                    tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, bd0 + k * w_k16, idesc2, (first | k) != 0);
 #pragma unroll
-                for (int k = 0; k < TC_KS / 16; ++k) {
-                  uint64_t ad = smem_desc(a_row + (uint32_t)((ah * (TC_KS / 8) + 2 * k) * Cfg::PLANE), Cfg::PLANE, 128);
-                  uint64_t bd = smem_desc(w_st + (uint32_t)(wh * (TC_KS / 8) + 2 * k) * w_lbo, w_lbo, 128);
-                  tc_mma(d0 + (uint32_t)(m * cout), ad, bd, idesc, (s | t | pass | k) != 0);
+                  for (int k = 0; k < TC_KS / 16; ++k)
+                    tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, bd0 + k * w_k16, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int m = 0; m < T; ++m) {
+#pragma unroll
+                  for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
+#pragma unroll
+                    for (int k = 0; k < TC_KS / 16; ++k)
+                      tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0),
+                             bd0 + k * w_k16 + (pass == 2 ? w_lo16 : 0), idesc, (first | pass | k) != 0);
+                  }
                 }
               }
+              tc_commit(&B->w_empty[ws]);                  // stage reusable once these MMAs retire
+              if (last_tap) tc_commit(&B->a_empty[ab]);
+              if (last_tap && s == nslabs - 1) tc_commit(&B->t_full[tb]);
             }
-            tc_commit(&B->w_empty[ws]);                    // stage reusable once these MMAs retire
+            __syncwarp();
             if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
           }
-          tc_commit(&B->a_empty[ab]);
-          if (++ab == 2) { ab = 0; aph ^= 1; }
         }
-        tc_commit(&B->t_full[tb]);
-        if (++tb == nbuf) { tb = 0; tph ^= 1; }
+        if (++ab == 2) { ab = 0; aph ^= 1; }
       }
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: all MMAs issued
+      if (++tb == nbuf) { tb = 0; tph ^= 1; }
     }
   } else {
     // ===================== epilogue: TMEM -> bias / ELU / hi-lo split -> HBM =====================
-    // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); they
-    // take alternate M tiles.  All arithmetic is on values pre-scaled by ACT_SCALE.
+    // Four warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); the
+    // (M tile, 16-column) units of a group are dealt round-robin to them.  All arithmetic is
+    // on values pre-scaled by ACT_SCALE.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    int tb = 0, tph = 0;
-    const long long row_end = L.row0 + L.nrows;
+    const int sub = (warp - 2) >> 2;
+    const int nc = cout >> 4;                               // 16-column units per tile
+    int tb = 0, tph = 0, dn = 0;
+    unsigned long long* edbg = (warp == 2 && lane == 0) ? L.dbg : nullptr;
+    const uint32_t nrows = (uint32_t)L.nrows;
     constexpr float K_ACC = OUT_SCALE * ACT_SCALE;          // accumulator -> scaled activation
     constexpr float K_L2E = 1.4426950408889634f / ACT_SCALE;
     for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
       mbar_wait(&B->t_full[tb], tph);
       tc_fence_after();
-      for (int m = half; m < T; m += 2) {
-        const long long row = L.row0 + (long long)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
-        const long long q = row - L.row0;
-        const int within = (int)(q % L.per_board);
-        const int rr = within / L.pitch, cc = within % L.pitch;
-        const bool real = row < row_end && rr < L.S && cc < L.S;
-        for (int c0 = 0; c0 < cout; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cout + m * cout + c0), v);
-          float f[32];
+      dbg_mark(edbg, 2, dn);                               // accumulators ready
+      int cur_m = -1;
+      bool real = false;
+      uint32_t q = 0;
+      for (int u = sub; u < T * nc; u += TC_EPI_WARPS / 4) {
+        const int m = u / nc, c0 = (u - m * nc) << 4;
+        if (m != cur_m) {
+          cur_m = m;
+          q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
+          const uint32_t within = q % (uint32_t)L.per_board;
+          const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+          real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+        }
+        const long long row = L.row0 + q;
+        uint32_t v[16];
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + c0);
+        tc_ld16(taddr, v);
+        if (L.fold) {                                         // + a_hi * w_lo partial sums
+          uint32_t v2[16];
+          tc_ld16(taddr + (uint32_t)cout, v2);
+          tc_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tc_ld_wait();
+        }
+        float f[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
-              const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
-              f[4 * e + j] = x > 0.0f ? x : neg;
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+            const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+            f[4 * e + j] = x > 0.0f ? x : neg;
+          }
+        }
+        if (L.out) {
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
+              const __half2 h = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              hi[e] = real ? *(const uint32_t*)&h : 0u;
+              lo[e] = real ? *(const uint32_t*)&l : 0u;
             }
+            const long long chunk = (c0 >> 3) + kc;
+            __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
+            __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
+            *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          if (L.out) {
+        }
+        if (L.out_f32 && q < nrows) {
+          constexpr float inv = 1.0f / ACT_SCALE;
+          float4* po = (float4*)(L.out_f32 + row * cout + c0);
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
-                const __half2 h = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                hi[e] = real ? *(const uint32_t*)&h : 0u;
-                lo[e] = real ? *(const uint32_t*)&l : 0u;
-              }
-              const long long chunk = (c0 >> 3) + kc;
-              __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
-              __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
-              *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-          if (L.out_f32 && row < row_end) {
-            constexpr float inv = 1.0f / ACT_SCALE;
-            float4* po = (float4*)(L.out_f32 + row * cout + c0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int e = 0; e < 4; ++e)
+            po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       tc_fence_before();
       __syncwarp();
+      dbg_mark(edbg, 2, dn);                               // tile(s) drained
       if (lane == 0) mbar_arrive(&B->t_empty[tb]);
       if (++tb == nbuf) { tb = 0; tph ^= 1; }
     }
@@ -387,7 +484,8 @@ __global__ void __launch_bounds__(128) k_tc_conv1(const int8_t* __restrict__ pla
 }
 
 // TF kernel [taps][cin][cout] (+ optional res [1][rcin][cout]) -> per-(slab, tap) stages
-// [hi|lo][kchunk 4][cout][8] fp16, scaled by 2^10.
+// [kchunk 4][hi|lo][cout][8] fp16, scaled by 2^10 (hi and lo adjacent along N, so one
+// N = 2*cout descriptor covers both).
 __global__ void k_tc_pack(const float* __restrict__ w, const float* __restrict__ wres, int ntaps, int cin, int rcin,
                           int cout, __half* __restrict__ out) {
   const int main_stages = (cin / TC_KS) * ntaps;
@@ -410,8 +508,8 @@ __global__ void k_tc_pack(const float* __restrict__ w, const float* __restrict__
     x *= W_SCALE;
     const __half h = __float2half_rn(x);
     __half* base = out + (size_t)stage * 2 * per_stage;
-    base[((size_t)j * cout + n) * 8 + e] = h;
-    base[per_stage + ((size_t)j * cout + n) * 8 + e] = __float2half_rn(x - __half2float(h));
+    base[(((size_t)j * 2 + 0) * cout + n) * 8 + e] = h;
+    base[(((size_t)j * 2 + 1) * cout + n) * 8 + e] = __float2half_rn(x - __half2float(h));
   }
 }
 
@@ -447,7 +545,7 @@ struct a5_tc_state {
   __half* act[11] = {};
   __half* wpk[11] = {};
   long long plane_rows = 0;
-  int t128 = 2;
+  int t128 = 4, t64 = 2, fold = 1;
   int num_sms = 0;
 };
 
@@ -476,8 +574,11 @@ int tc_alloc(a5_net* net) {
   }
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
-  const char* t128 = getenv("A5_TC_T128");              // tuning knob: M tiles per group for Cout = 128
-  tc->t128 = (t128 && atoi(t128) == 4) ? 4 : 2;
+  // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
+  const char* ev;
+  tc->t128 = ((ev = getenv("A5_TC_T128")) && atoi(ev) == 2) ? 2 : 4;
+  tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
+  tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
   int dev = 0;
   A5_CUDA(cudaGetDevice(&dev));
   A5_CUDA(cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -507,6 +608,7 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
 
 // profiling hook (a5__debug_layer_times): when set, an event is recorded after every launch group
 static cudaEvent_t* g_tc_events = nullptr;
+static unsigned long long* g_tc_dbg = nullptr;   // a5__debug_timeline: [10 layers][4 roles][256]
 #define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
 
 // heads + biases come from the fp32 path's packed copies (fp32_set_weights runs first)
@@ -533,7 +635,9 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
-    const int T = (D.cout == 128) ? tc->t128 : 4;
+    const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
+    L.fold = (D.cout <= 64) ? tc->fold : 0;
+    L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 4 * 256 : nullptr;
     const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows; L.ngroups = ngroups;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
@@ -552,6 +656,18 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
 
 extern "C" {
 int a5_net_tc_available(void) { return 1; }
+
+// internal tooling: clock64 timeline of CTA 0 for every conv layer of one forward;
+// d_dbg = uint64 [10][4][256] (zeroed by the caller): roles 0 producer, 1 MMA issuer (groups/slabs),
+// 2 epilogue warp 2, 3 MMA issuer (weight stages: wait, landed).
+int a5__debug_timeline(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value,
+                       unsigned long long* d_dbg, void* stream) {
+  A5_ARG(net && d_planes && d_dbg);
+  g_tc_dbg = d_dbg;
+  int rc = tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream);
+  g_tc_dbg = nullptr;
+  return rc;
+}
 
 // internal tooling (not part of alphafive.h): average milliseconds of each launch group of the
 // tensor-core forward over `reps` runs: h_ms[0] conv1, h_ms[1..10] block convs, h_ms[11] heads.
