@@ -1,5 +1,6 @@
 // a5_net: device state of the policy/value network (both compute paths).
 #pragma once
+#include <cuda_fp16.h>
 #include "net_common.cuh"
 
 struct a5_tc_state;   // tensor-core path (net_tc.cu)
@@ -29,6 +30,15 @@ void fp32_free(a5_net* net);
 int fp32_set_weights(a5_net* net, const float* const* t, cudaStream_t st);
 int fp32_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st);
 int fp32_heads(a5_net* net, int n, float* prob, float* value, cudaStream_t st);
+
+struct HeadsState;
+int heads_alloc(a5_net* net, HeadsState** out);
+void heads_free(HeadsState* h);
+int heads_set_weights(a5_net* net, HeadsState* h, const float* const* t, cudaStream_t st);
+int heads_forward(a5_net* net, HeadsState* h, int n, float* prob, float* value, cudaStream_t st);
+// conv-epilogue side of the heads: where the fused 1x1 head convs write, and their weights
+struct HeadsIO { __half* a_pol; __half* a_val; const float* pconv_w; const float* pconv_b; int nst_pol, nst_val; };
+HeadsIO heads_io(const HeadsState* h);
 
 int tc_alloc(a5_net* net);
 void tc_free(a5_net* net);

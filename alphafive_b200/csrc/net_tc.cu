@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "net.cuh"
+#include "tc_ptx.cuh"
 
 namespace a5 {
 
@@ -32,10 +33,6 @@ constexpr int TC_KS = 32;               // channels per slab
 constexpr int TC_WSTAGE_MAX = 2 * (TC_KS / 8) * 128 * 16;   // 16 KB (Cout = 128)
 constexpr int TC_EPI_WARPS = 16;        // four per TMEM lane quadrant
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr float ACT_SCALE = 16.0f;      // 2^4
-constexpr float W_SCALE = 1024.0f;      // 2^10
-constexpr float OUT_SCALE = 1.0f / (16.0f * 1024.0f);
-
 // T = M tiles (of 128 positions) per group; a group shares every weight stage.
 template <int T>
 struct TCfg {
@@ -44,7 +41,7 @@ struct TCfg {
   static constexpr int PLANE = SROWS * 16;             // bytes per (kchunk) plane in smem
   static constexpr int SLAB = 2 * (TC_KS / 8) * PLANE; // hi+lo, 4 kchunks
   static constexpr int WSTAGES = T >= 4 ? 4 : 8;
-  static constexpr int SMEM = 2 * SLAB + WSTAGES * TC_WSTAGE_MAX + 128 * 4 + 256 + 128;
+  static constexpr int SMEM = 2 * SLAB + WSTAGES * TC_WSTAGE_MAX + 128 * 4 + 256 + (32 * 16 + 16) * 4 + 128;
 };
 
 struct TCLayer {
@@ -57,6 +54,14 @@ struct TCLayer {
   int cout, ntaps;
   int fold;                      // 1: hi*[Whi|Wlo] as one N = 2*cout MMA (cout <= 64)
   unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
+  // fused 1x1 head conv + ELU in the epilogue (network.py:69-70 value, :81-82 policy): the
+  // layer's own activation is then not stored; the head output goes out as the A operand of
+  // the dense layer that follows (k_tc_fc), K ordered (cell, channel).
+  int head_ch;                   // 0 none, 4 value head, 16 policy head
+  const float* head_w;           // f32 [32][head_ch]
+  const float* head_b;           // f32 [head_ch]
+  __half* head_out;              // [mtile][stage][hi|lo][kchunk 4][128 boards][8]
+  int head_nst;                  // K stages (of 32) per board row
   int shifts[9];
   long long plane_rows;          // rows per channel-chunk plane in HBM (incl. guards)
   long long row0;                // first valid row (guard)
@@ -65,114 +70,12 @@ struct TCLayer {
   int S, pitch, per_board;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (spin > (1u << 26)) __trap();      // a lost arrival must fail loudly, not hang the GPU
-  }
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return done != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start >> 4 | [16,30) leading-dim byte offset >> 4 (K-adjacent core matrices)
-//   [32,46) stride byte offset >> 4 (8-row groups) | [46,48) version = 1 | [61,64) layout = 0
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = f16, K-major both.
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 struct __align__(8) TCBarriers {
   uint64_t a_full[2], a_empty[2], w_full[8], w_empty[8], t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
 static_assert(sizeof(TCBarriers) <= 256, "barrier block outgrew its smem reservation");
-
-// exp(x) - 1 for x <= 0 through ex2.approx (abs error ~1e-7: below the fp32 rounding of the
-// O(1) activations it feeds); expm1f costs ~10x the issue slots in the epilogue.
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int role, int& n) {
   if (dbg && blockIdx.x == 0 && n < 256) dbg[role * 256 + n++] = clock64();
@@ -187,6 +90,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
   uint8_t* w_buf = smem + 2 * Cfg::SLAB;                   // WSTAGES stages
   float* s_bias = (float*)(w_buf + Cfg::WSTAGES * TC_WSTAGE_MAX);
   TCBarriers* B = (TCBarriers*)(s_bias + 128);
+  float* s_hw = (float*)((uint8_t*)B + 256);              // head conv weights [32][head_ch], then bias * ACT_SCALE
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cout = L.cout;
@@ -197,6 +101,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
   const uint32_t stage_bytes = 2u * (TC_KS / 8) * cout * 16u;
 
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
+  if (L.head_ch) {
+    for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
+    if (threadIdx.x < L.head_ch) s_hw[32 * 16 + threadIdx.x] = L.head_b[threadIdx.x] * ACT_SCALE;
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&B->a_full[i], 1); mbar_init(&B->a_empty[i], 1); }
     for (int i = 0; i < Cfg::WSTAGES; ++i) { mbar_init(&B->w_full[i], 1); mbar_init(&B->w_empty[i], 1); }
@@ -351,10 +259,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
       mbar_wait(&B->t_full[tb], tph);
       tc_fence_after();
       dbg_mark(edbg, 2, dn);                               // accumulators ready
+      if (L.head_ch) {
+        // head layers (cout = 32): a warp takes whole rows of one M tile, so the 1x1 head conv
+        // sees all 32 channels of its position.
+        for (int m = sub; m < T; m += TC_EPI_WARPS / 4) {
+          const uint32_t q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
+          const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
+          const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+          const bool real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+          float f[32];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + h2 * 16);
+            tc_ld16(taddr, v);
+            if (L.fold) {
+              uint32_t v2[16];
+              tc_ld16(taddr + (uint32_t)cout, v2);
+              tc_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+            } else {
+              tc_ld_wait();
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 b4 = *(const float4*)&s_bias[h2 * 16 + 4 * e];
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+                const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+                f[h2 * 16 + 4 * e + j] = x > 0.0f ? x : neg;       // ACT_SCALE * activation
+              }
+            }
+          }
+          if (real) {
+            const uint32_t cell = rr * (uint32_t)L.S + cc;
+            const uint32_t mt = board >> 7, brow = board & 127u;
+            if (L.head_ch == 16) {
+              float acc[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc[c] = s_hw[32 * 16 + c];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  const float4 w4 = *(const float4*)&s_hw[k * 16 + 4 * c4];
+                  acc[4 * c4 + 0] = fmaf(f[k], w4.x, acc[4 * c4 + 0]);
+                  acc[4 * c4 + 1] = fmaf(f[k], w4.y, acc[4 * c4 + 1]);
+                  acc[4 * c4 + 2] = fmaf(f[k], w4.z, acc[4 * c4 + 2]);
+                  acc[4 * c4 + 3] = fmaf(f[k], w4.w, acc[4 * c4 + 3]);
+                }
+              }
+              // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8
+              __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
+#pragma unroll
+              for (int c8 = 0; c8 < 2; ++c8) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = acc[c8 * 8 + 2 * e], a1 = acc[c8 * 8 + 2 * e + 1];
+                  const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                  const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                  const __half2 h = __floats2half2_rn(x0, x1);
+                  const float2 hf = __half22float2(h);
+                  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                  hi[e] = *(const uint32_t*)&h;
+                  lo[e] = *(const uint32_t*)&l;
+                }
+                *(uint4*)(base + (size_t)c8 * 128 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *(uint4*)(base + (size_t)(4 + c8) * 128 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            } else {
+              float acc[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[c] = s_hw[32 * 16 + c];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float4 w4 = *(const float4*)&s_hw[k * 4];
+                acc[0] = fmaf(f[k], w4.x, acc[0]);
+                acc[1] = fmaf(f[k], w4.y, acc[1]);
+                acc[2] = fmaf(f[k], w4.z, acc[2]);
+                acc[3] = fmaf(f[k], w4.w, acc[3]);
+              }
+              // k = cell*4 + c -> stage = cell/8, kchunk = (cell%8)/2, element = (cell%2)*4 + c
+              __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 3)) * 2) * 4 + ((cell & 7u) >> 1)) * 128 * 8 +
+                             brow * 8 + (cell & 1u) * 4;
+              uint32_t hi[2], lo[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
+                const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[e] = *(const uint32_t*)&h;
+                lo[e] = *(const uint32_t*)&l;
+              }
+              *(uint2*)base = make_uint2(hi[0], hi[1]);
+              *(uint2*)(base + (size_t)4 * 128 * 8) = make_uint2(lo[0], lo[1]);
+            }
+          }
+        }
+      }
       int cur_m = -1;
       bool real = false;
       uint32_t q = 0;
-      for (int u = sub; u < T * nc; u += TC_EPI_WARPS / 4) {
+      for (int u = sub; !L.head_ch && u < T * nc; u += TC_EPI_WARPS / 4) {
         const int m = u / nc, c0 = (u - m * nc) << 4;
         if (m != cur_m) {
           cur_m = m;
@@ -433,53 +446,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
 }
 
 // ------------------------------------------------------------------ support kernels
-// conv1 (5x5, 3->32, ELU) from the int8 planes into the tensor-core activation layout.
-__global__ void __launch_bounds__(128) k_tc_conv1(const int8_t* __restrict__ planes, const float* __restrict__ W,
-                                                 const float* __restrict__ bias, __half* __restrict__ out,
-                                                 long long plane_rows, int S, int pitch, int per_board, int guard) {
-  __shared__ float sw[75 * 32];
-  __shared__ int8_t sp[3][20][20];
-  const int b = blockIdx.x, tid = threadIdx.x, C = S * S;
-  for (int i = tid; i < 75 * 32; i += 128) sw[i] = W[(i / 32) * 64 + (i % 32)];
-  for (int i = tid; i < 3 * 20 * 20; i += 128) ((int8_t*)sp)[i] = 0;
+// conv1 (5x5, 3->32, ELU; network.py:63) from the int8 planes into the tensor-core activation
+// layout.  The inputs are {0,1} (utils.py:256-272), so a kernel row applied to a window row is
+// one of 32 possible partial sums: a table T[plane][ky][5-bit pattern][32 ch] is built in shared
+// memory once per (persistent) CTA, board rows are kept as bit masks, and every output is
+// bias + 15 table rows -- no multiplies, no data-dependent branches.
+constexpr int C1_THREADS = 256;
+constexpr int C1_NB = 4;                        // boards per CTA iteration
+constexpr int C1_SMEM = (15 * 32 * 32 + 75 * 32 + 32) * 4 + C1_NB * 3 * (A5_MAX_BOARD + 4) * 4;
+
+__global__ void __launch_bounds__(C1_THREADS) k_tc_conv1(const int8_t* __restrict__ planes, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, __half* __restrict__ out,
+                                                        long long plane_rows, int S, int pitch, int per_board, int guard,
+                                                        int n) {
+  extern __shared__ __align__(16) float c1_smem[];
+  float* tab = c1_smem;                         // [3][5][32][32]
+  float* sw = tab + 15 * 32 * 32;               // [75][32] staging of the TF kernel
+  float* sb = sw + 75 * 32;
+  uint32_t (*rowmask)[3][A5_MAX_BOARD + 4] = (uint32_t (*)[3][A5_MAX_BOARD + 4])(sb + 32);
+  const int tid = threadIdx.x, C = S * S;
+  for (int i = tid; i < 75 * 32; i += C1_THREADS) sw[i] = W[(i / 32) * 64 + (i % 32)];   // packed ldw = 64
+  if (tid < 32) sb[tid] = bias[tid];
   __syncthreads();
-  for (int i = tid; i < 3 * C; i += 128) {
-    int ch = i / C, cell = i % C;
-    sp[ch][cell / S + 2][cell % S + 2] = planes[(size_t)b * 3 * C + i];
+  for (int i = tid; i < 15 * 32 * 32; i += C1_THREADS) {
+    const int pat = i & 31, ch = (i >> 5) & 31, pk = i >> 10;      // pk = p*5 + ky; [pk][ch][pat]: lanes differ in pat -> no bank conflicts
+    const int p = pk / 5, ky = pk - p * 5;
+    float acc = 0.0f;
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx)
+      if ((pat >> kx) & 1) acc += sw[((ky * 5 + kx) * 3 + p) * 32 + ch];
+    tab[i] = acc;
   }
-  __syncthreads();
-  // thread = (position, channel-chunk of 8): 16-byte stores
-  for (int idx = tid; idx < per_board * 4; idx += 128) {
-    const int pos = idx >> 2, kc = idx & 3;
-    const int rr = pos / pitch, cc = pos % pitch;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-    if (rr < S && cc < S) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = bias[kc * 8 + e];
-      for (int ky = 0; ky < 5; ++ky)
-        for (int kx = 0; kx < 5; ++kx)
-#pragma unroll
-          for (int ci = 0; ci < 3; ++ci)
-            if (sp[ci][rr + ky][cc + kx]) {
-              const float* wp = &sw[((ky * 5 + kx) * 3 + ci) * 32 + kc * 8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += wp[e];
-            }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = elu(v[e]);
+  constexpr float K_L2E = 1.4426950408889634f;
+  for (int b0 = blockIdx.x * C1_NB; b0 < n; b0 += gridDim.x * C1_NB) {
+    __syncthreads();
+    for (int i = tid; i < C1_NB * 3 * (A5_MAX_BOARD + 4); i += C1_THREADS) ((uint32_t*)rowmask)[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < C1_NB * 3 * S; i += C1_THREADS) {   // one thread per (board, plane, row): bit (x + 2)
+      const int bb = i / (3 * S), pr = i - bb * 3 * S;
+      const int p = pr / S, y = pr - p * S;
+      if (b0 + bb < n) {
+        const int8_t* src = planes + (size_t)(b0 + bb) * 3 * C + p * C + y * S;
+        uint32_t m = 0;
+        for (int x = 0; x < S; ++x) m |= (src[x] != 0 ? 1u : 0u) << (x + 2);
+        rowmask[bb][p][y + 2] = m;
+      }
     }
-    __half hi[8], lo[8];
+    __syncthreads();
+    const int ppad = (per_board + 31) & ~31;     // lanes of a warp = 32 consecutive positions of one (board, chunk)
+    const int items = ppad * 4;
+    for (int i = tid; i < C1_NB * items; i += C1_THREADS) {
+      const int bb = i / items, it = i - bb * items;
+      const int kc = it / ppad, pos = it - kc * ppad;
+      if (b0 + bb >= n) break;
+      if (pos >= per_board) continue;
+      const int rr = pos / pitch, cc = pos - rr * pitch;
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float x = v[e] * ACT_SCALE;
-      hi[e] = __float2half_rn(x);
-      lo[e] = __float2half_rn(x - __half2float(hi[e]));
+      for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+      if (rr < S && cc < S) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = sb[kc * 8 + e];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const uint32_t pat = (rowmask[bb][p][rr + ky] >> cc) & 31u;
+            const float* tp = &tab[((p * 5 + ky) * 32 + kc * 8) * 32 + pat];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += tp[e * 32];
+          }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : ex2_approx(v[e] * K_L2E) - 1.0f;
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = v[2 * e] * ACT_SCALE, x1 = v[2 * e + 1] * ACT_SCALE;
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        hi[e] = *(const uint32_t*)&h;
+        lo[e] = *(const uint32_t*)&l;
+      }
+      const long long row = guard + (long long)(b0 + bb) * per_board + pos;
+      *(uint4*)(out + ((long long)kc * plane_rows + row) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *(uint4*)(out + ((long long)(4 + kc) * plane_rows + row) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    const long long row = guard + (long long)b * per_board + pos;
-    *(uint4*)(out + ((long long)kc * plane_rows + row) * 8) = *(uint4*)hi;
-    *(uint4*)(out + ((long long)(4 + kc) * plane_rows + row) * 8) = *(uint4*)lo;
   }
 }
 
@@ -547,6 +600,7 @@ struct a5_tc_state {
   long long plane_rows = 0;
   int t128 = 4, t64 = 2, fold = 1;
   int num_sms = 0;
+  a5::HeadsState* heads = nullptr;
 };
 
 namespace a5 {
@@ -572,6 +626,7 @@ int tc_alloc(a5_net* net) {
     size_t stages = (size_t)(L.cin / TC_KS) * 9 + (L.res_src >= 0 ? L.res_cin / TC_KS : 0);
     A5_CUDA(cudaMalloc(&tc->wpk[l], stages * 2 * TC_KS * L.cout * sizeof(__half)));
   }
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
@@ -579,6 +634,8 @@ int tc_alloc(a5_net* net) {
   tc->t128 = ((ev = getenv("A5_TC_T128")) && atoi(ev) == 2) ? 2 : 4;
   tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
+  int hrc = heads_alloc(net, &tc->heads);
+  if (hrc) return hrc;
   int dev = 0;
   A5_CUDA(cudaGetDevice(&dev));
   A5_CUDA(cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -589,6 +646,7 @@ void tc_free(a5_net* net) {
   if (!net->tc) return;
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->act[i]);
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk[i]);
+  heads_free(net->tc->heads);
   delete net->tc;
   net->tc = nullptr;
 }
@@ -603,11 +661,12 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     k_tc_pack<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, tc->wpk[l]);
     A5_CUDA(cudaGetLastError());
   }
-  return A5_OK;
+  return heads_set_weights(net, tc->heads, t, st);
 }
 
 // profiling hook (a5__debug_layer_times): when set, an event is recorded after every launch group
 static cudaEvent_t* g_tc_events = nullptr;
+static bool g_tc_keep_head_acts = false;           // a5__debug_activation wants block3/5 outputs stored too
 static unsigned long long* g_tc_dbg = nullptr;   // a5__debug_timeline: [10 layers][4 roles][256]
 #define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
 
@@ -616,8 +675,10 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   a5_tc_state* tc = net->tc;
   PosSpace ps(net->S);
   TC_MARK(0);
-  k_tc_conv1<<<n, 128, 0, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
-                               ps.per_board, ps.guard);
+  const int nb1 = (n + C1_NB - 1) / C1_NB;
+  const int grid1 = nb1 < 3 * tc->num_sms ? nb1 : 3 * tc->num_sms;
+  k_tc_conv1<<<grid1, C1_THREADS, C1_SMEM, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
+                                   ps.per_board, ps.guard, n);
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
@@ -630,7 +691,16 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     L.wpk = tc->wpk[l];
     L.bias = net->bias[l];
     L.out = tc->act[D.out];
-    L.out_f32 = (l == 6) ? net->act[B3O] : (l == 10) ? net->act[B5O] : nullptr;   // heads read fp32 rows
+    L.out_f32 = nullptr;
+    if (l == 6 || l == 10) {          // block3 / block5 outputs feed only the heads: fused 1x1 conv, nothing else stored
+      const HeadsIO io = heads_io(tc->heads);
+      L.out = g_tc_keep_head_acts ? L.out : nullptr;
+      L.head_ch = l == 6 ? 4 : 16;
+      L.head_w = l == 6 ? net->vconv_w : io.pconv_w;
+      L.head_b = l == 6 ? net->vconv_b : io.pconv_b;
+      L.head_out = l == 6 ? io.a_val : io.a_pol;
+      L.head_nst = l == 6 ? io.nst_val : io.nst_pol;
+    }
     L.cout = D.cout; L.ntaps = 9;
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
@@ -647,7 +717,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
   }
-  int rc = fp32_heads(net, n, prob, value, st);
+  int rc = heads_forward(net, tc->heads, n, prob, value, st);
   TC_MARK(12);
   return rc;
 }
@@ -656,6 +726,10 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
 
 extern "C" {
 int a5_net_tc_available(void) { return 1; }
+
+// internal tooling: also store the block3 / block5 activations (normally consumed in-register by
+// the fused head convs) so a5__debug_activation can show them.
+int a5__debug_keep_head_acts(int on) { g_tc_keep_head_acts = on != 0; return A5_OK; }
 
 // internal tooling: clock64 timeline of CTA 0 for every conv layer of one forward;
 // d_dbg = uint64 [10][4][256] (zeroed by the caller): roles 0 producer, 1 MMA issuer (groups/slabs),

@@ -32,6 +32,7 @@ for i, ch in enumerate(chs):
     out = torch.empty((n * pb, ch), dtype=torch.float32, device="cuda")
     check(lib.a5__debug_activation(net.handle, 0, i, n, ptr(out), stream_ptr()))
     acts0.append(out.clone())
+lib.a5__debug_keep_head_acts(1)
 p1, v1 = net.forward(planes, mode=1)
 torch.cuda.synchronize()
 print("tc forward done")
