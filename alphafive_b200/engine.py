@@ -193,18 +193,4 @@ def _view(p, shape, dtype, device) -> torch.Tensor:
     return torch.as_tensor(_DevView(p, shape, dtype), device=device)
 
 
-def parse_records(buf: torch.Tensor, S: int):
-    """Harvested records -> list of dicts with numpy fields (host side)."""
-    host = buf.cpu().numpy()
-    Cc = S * S
-    bb = (Cc + 15) // 16 * 16
-    hs = C.sizeof(RecordHeader)
-    out = []
-    for row in host:
-        h = RecordHeader.from_buffer_copy(row[:hs].tobytes())
-        board = row[hs:hs + Cc].view(np.int8).reshape(S, S).copy()
-        policy = row[hs + bb:hs + bb + 4 * Cc].view(np.float32).reshape(S, S).copy()
-        out.append(dict(game_id=h.game_id, game_serial=h.game_serial, ply=h.ply, game_len=h.game_len,
-                        last_action=h.last_action, value=h.value, weight=h.weight, result=h.result,
-                        board=board, policy=policy))
-    return out
+from .replay import parse_records  # noqa: E402,F401  (kept importable from here)

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from . import rules
-from .engine import SearchEngine, make_config, parse_records
+from .engine import SearchEngine, make_config
+from .replay import gather_records, parse_records, records_to_games
 from .net import DeviceNet
 
 
@@ -79,24 +80,14 @@ class SelfPlay:
         buf, _ = self.harvest()
         return records_to_games(parse_records(buf, self.S), self.S)
 
+    def harvest_all_ranks(self, group=None):
+        """Harvest this rank's finished-ply records and gather every rank's (NCCL allgather over
+        NVLink; the one collective of the path).  Returns (records uint8 [total, stride], counts)."""
+        buf, _ = self.harvest()
+        return gather_records(buf, group=group)
+
     def counters(self):
         return self.engine.counters()
-
-
-def records_to_games(recs, S):
-    from .genData.player import board_to_state
-    by = {}
-    for r in recs:
-        by.setdefault((r["game_id"], r["game_serial"]), []).append(r)
-    games = []
-    for key in sorted(by):
-        plies = sorted(by[key], key=lambda r: r["ply"])
-        rec = []
-        for r in plies:
-            la = None if r["last_action"] < 0 else (r["last_action"] // S, r["last_action"] % S)
-            rec.append((board_to_state(r["board"]), r["policy"], la, float(r["value"]), np.float32(r["weight"])))
-        games.append((rec, int(plies[0]["result"])))
-    return games
 
 
 class BatchedPlayer:
