@@ -60,6 +60,17 @@ class SelfPlay:
                 with torch.cuda.graph(self._graph):     # capture only: nothing executes here
                     self._pass()
 
+    def set_budget(self, sims: int, upper: int):
+        """config.simulation_per_step / upper_simulation_per_step for the moves that start from
+        now on (the reference reads them lazily per get_action).  Kernel parameters are baked
+        into the captured graph, so the pass is re-captured."""
+        self.engine.set_budget(sims, upper)
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._pass()
+
     def run_passes(self, k: int):
         self.start()
         if self._graph is not None:

@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--upper", type=int, default=None)
     ap.add_argument("--net-mode", default=os.environ.get("A5_NET_MODE", "auto"), choices=["auto", "fp32", "tc"])
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--preroll-moves", type=int, default=48,
+                    help="untimed moves at --preroll-sims before the warm-up, so games are spread over all plies")
+    ap.add_argument("--preroll-sims", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
@@ -205,6 +208,14 @@ def run_ours(a):
         return buf.shape[0], games
 
     sp.start()
+    if a.preroll_moves > 0:
+        # Desynchronise the games: a short-budget prefix plays ~preroll_moves plies per game (games
+        # finish and restart on the way), so the warm-up and the timed steps see the steady-state mix
+        # of openings, middle games, terminal positions and record emission -- not 4096 empty boards.
+        sp.set_budget(a.preroll_sims, a.preroll_sims + 10)
+        sp.run_passes(a.preroll_moves * a.preroll_sims)
+        sp.harvest()
+        sp.set_budget(sims, upper)
     for _ in range(a.warmup):
         one_step(False)
     c0 = sp.counters()
@@ -237,6 +248,7 @@ def run_ours(a):
         nn_ms += tn0.elapsed_time(tn1); tree_ms += tt0.elapsed_time(tt1)
     nn_ms /= reps; tree_ms /= reps
     c2 = sp.counters()
+    lt = layer_times(net, sp.engine.planes_ptr, N, prob, val) if mode == _lib.NET_TC else None
 
     t = torch.tensor([ms, float(c1["moves"] - c0["moves"]), float(c1["leaf_evals"] - c0["leaf_evals"]),
                       float(c1["sims"] - c0["sims"]), float(c1["games"] - c0["games"])], dtype=torch.float64, device="cuda")
@@ -297,14 +309,12 @@ def run_ours(a):
             "config": {"workload": workload_name(a, world), "board": S, "sims": sims, "upper_sims": upper,
                        "games_per_gpu": N, "net_mode": "fp32" if mode == _lib.NET_FP32 else "tc",
                        "l2": "per-pass working set (activations + node arenas) exceeds the 126 MB L2",
-                       "cuda_graph": not a.no_graph, "step": f"{sims} lock-step passes"},
+                       "cuda_graph": not a.no_graph, "step": f"{sims} lock-step passes",
+                       "preroll": f"{a.preroll_moves} untimed moves at {a.preroll_sims} sims to spread games over all plies"},
             "e2e": {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": bp.h2d_bytes,
                     "d2h_bytes_per_step": bp.d2h_bytes, "api": "BatchedPlayer.get_actions(host boards) + device step/terminal"},
             "gpu_launches": int((c1["passes"] - c0["passes"]) * (launches_per_pass(mode) + 1)),
-            "roofline": {"bound": "tensor", "kernel": "policy/value net forward (all conv/dense launches of one pass)",
-                         "achieved": nn_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nn_tflops / pk["tensor"],
-                         "peak_source": pk["src"] + " bf16 sustained", "traffic": None,
-                         "ms_per_launch_group": nn_ms, "flop_per_leaf": flop},
+            "roofline": roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk),
             "roofline_tree": {"bound": "hbm", "kernel": "k_step (tree pass)", "achieved": tree_gbs, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": tree_gbs / pk["hbm"], "ms_per_launch": tree_ms,
                               "bytes_per_sim": bytes_per_sim, "d_bar": dbar, "a_bar": abar, "f_leaf": fleaf},
@@ -314,8 +324,9 @@ def run_ours(a):
         if not a.no_cpu_baseline:
             cores = max(1, min((os.cpu_count() or 1) - 1, 64))
             v, ev, wall = cpu_moves_per_sec(S, sims, upper, cores, 2)
+            v5, ev5, _ = cpu_moves_per_sec(S, sims, upper, min(5, cores), 2)     # config.py:20 max_processes = 5
             out["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-                                   "leaf_evals_per_s": ev,
+                                   "leaf_evals_per_s": ev, "five_workers": {"value": v5, "leaf_evals_per_s": ev5},
                                    "sample": f"{cores} processes x 2 moves of {sims} sims from the empty board, oracle port "
                                              f"(numpy MCTS + torch-CPU fp32 net, 1 thread each), {wall:.1f}s wall"}
         print(json.dumps(out), flush=True)
@@ -323,9 +334,57 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
+    """Dominant kernel = k_tc_conv (ten launches per pass, 98.9 % of the algorithmic FLOPs).
+    achieved = algorithmic conv FLOPs of one pass / summed CUDA-event time of its ten launches."""
+    whole = {"kernel": "whole net forward (12 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
+             "ms_per_pass": nn_ms, "flop_per_leaf": flop}
+    if lt is None:
+        return {"bound": "tensor", "kernel": "policy/value net forward, fp32 CUDA-core path", "achieved": nn_tflops,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nn_tflops / pk["tensor"],
+                "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
+    conv_ms = sum(lt[1:11])
+    conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
+    ach = conv_flop / (conv_ms / 1000) / 1e12
+    tr = measured_traffic()
+    return {"bound": "tensor", "kernel": "k_tc_conv (tcgen05 3x3 conv + residual, 10 launches per pass)",
+            "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+            "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
+            "traffic": tr.get("conv_dram_bytes_per_pass") if tr else None,
+            "traffic_note": tr.get("note") if tr else "no ncu capture committed for this build",
+            "algorithmic_flop_per_pass": conv_flop, "issued_flop_factor": 3,
+            "ms_per_pass": conv_ms, "ms_conv1": lt[0], "ms_heads": lt[11], "ms_layers": lt[1:11],
+            "whole_net": whole}
+
+
 def launches_per_pass(mode):
-    # conv1 + 10 block convs + value head + policy conv + policy fc + softmax (fp32 path)
-    return 15
+    # tensor-core path: conv1 + 10 block convs + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
+    return 12 if mode == 1 else 15
+
+
+CONV_MAC_PER_CELL = 485_376          # the ten 3x3(+1x1) block convs, MACs per board cell (58,730,496 @ 11x11)
+
+
+def layer_times(net, planes_ptr, N, prob, val, reps=10):
+    """CUDA-event time of every launch group of one net forward (ms): conv1, 10 block convs, heads."""
+    import ctypes as C
+    from alphafive_b200 import _lib
+    from alphafive_b200._lib import check, ptr, stream_ptr
+    fn = _lib.load().a5__debug_layer_times
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
+    ms = (C.c_float * 12)()
+    check(fn(net.handle, C.c_void_p(planes_ptr), N, reps, ptr(prob), ptr(val), ms, stream_ptr()))
+    return [float(x) for x in ms]
+
+
+def measured_traffic():
+    """DRAM bytes per pass of the block convs from the committed ncu capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":
