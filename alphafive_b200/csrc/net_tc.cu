@@ -32,7 +32,8 @@ constexpr int TC_HALO = 24;             // >= pitch + 1 for S <= 15, multiple of
 constexpr int TC_KS = 32;               // channels per slab
 constexpr int TC_WSTAGE_MAX = 2 * (TC_KS / 8) * 128 * 16;   // 16 KB (Cout = 128)
 constexpr int TC_EPI_WARPS = 16;        // four per TMEM lane quadrant
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_W_WARP = 2 + TC_EPI_WARPS;   // weight-stage producer (its own warp: slab prefetch must not wait on weight-ring credits)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;
 // T = M tiles (of 128 positions) per group; a group shares every weight stage.
 template <int T>
 struct TCfg {
@@ -71,14 +72,228 @@ struct TCLayer {
 };
 
 struct __align__(8) TCBarriers {
-  uint64_t a_full[2], a_empty[2], w_full[8], w_empty[8], t_full[2], t_empty[2];
+  uint64_t a_full[4], a_empty[4], w_full[8], w_empty[8], t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
 static_assert(sizeof(TCBarriers) <= 256, "barrier block outgrew its smem reservation");
 
+__device__ __forceinline__ unsigned long long dbg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));   // ns, comparable across SMs
+  return t;
+}
 __device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int role, int& n) {
-  if (dbg && blockIdx.x == 0 && n < 256) dbg[role * 256 + n++] = clock64();
+  if (dbg && blockIdx.x == 0 && n < 256) dbg[role * 256 + n++] = dbg_now();
+}
+// roles 4..6 (pair kernel): W producer of the leader, relay of the peer, W producer of the peer
+__device__ __forceinline__ void dbg_mark_cta(unsigned long long* dbg, int role, int& n, int cta) {
+  if (dbg && (int)blockIdx.x == cta && n < 256) dbg[role * 256 + n++] = dbg_now();
+}
+
+// ------------------------------------------------------------------ epilogue (shared by both conv kernels)
+// TMEM -> bias / ELU / hi-lo split -> HBM for the groups g_first, g_first + g_step, ... < g_end of
+// this CTA.  REMOTE: the "TMEM drained" arrival goes to the leader CTA of the pair.
+template <int T, bool REMOTE>
+__device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, const uint32_t tmem, const float* s_bias,
+                                            const float* s_hw, const int warp, const int lane, const int cpt,
+                                            const int nbuf, const int g_first, const int g_end, const int g_step) {
+  using Cfg = TCfg<T>;
+  const int cout = L.cout;
+  // ===================== epilogue: TMEM -> bias / ELU / hi-lo split -> HBM =====================
+  // Four warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); the
+  // (M tile, 16-column) units of a group are dealt round-robin to them.  All arithmetic is
+  // on values pre-scaled by ACT_SCALE.
+  const int quad = warp & 3;
+  const int sub = (warp - 2) >> 2;
+  const int nc = cout >> 4;                               // 16-column units per tile
+  int tb = 0, tph = 0, dn = 0;
+  unsigned long long* edbg = (warp == 2 && lane == 0) ? L.dbg : nullptr;
+  const uint32_t nrows = (uint32_t)L.nrows;
+  constexpr float K_ACC = OUT_SCALE * ACT_SCALE;          // accumulator -> scaled activation
+  constexpr float K_L2E = 1.4426950408889634f / ACT_SCALE;
+  for (int g = g_first; g < g_end; g += g_step) {
+    mbar_wait(&B->t_full[tb], tph);
+    tc_fence_after();
+    dbg_mark(edbg, 2, dn);                               // accumulators ready
+    if (L.head_ch) {
+      // head layers (cout = 32): a warp takes whole rows of one M tile, so the 1x1 head conv
+      // sees all 32 channels of its position.
+      for (int m = sub; m < T; m += TC_EPI_WARPS / 4) {
+        const uint32_t q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
+        const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
+        const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+        const bool real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+        float f[32];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + h2 * 16);
+          tc_ld16(taddr, v);
+          if (L.fold) {
+            uint32_t v2[16];
+            tc_ld16(taddr + (uint32_t)cout, v2);
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          } else {
+            tc_ld_wait();
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 b4 = *(const float4*)&s_bias[h2 * 16 + 4 * e];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+              const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+              f[h2 * 16 + 4 * e + j] = x > 0.0f ? x : neg;       // ACT_SCALE * activation
+            }
+          }
+        }
+        if (real) {
+          const uint32_t cell = rr * (uint32_t)L.S + cc;
+          const uint32_t mt = board >> 7, brow = board & 127u;
+          if (L.head_ch == 16) {
+            // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8; eight outputs at a time
+            __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
+#pragma unroll 1
+            for (int c8 = 0; c8 < 2; ++c8) {
+              float acc[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[c] = s_hw[32 * 16 + c8 * 8 + c];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float4 w0 = *(const float4*)&s_hw[k * 16 + c8 * 8];
+                const float4 w1 = *(const float4*)&s_hw[k * 16 + c8 * 8 + 4];
+                acc[0] = fmaf(f[k], w0.x, acc[0]); acc[1] = fmaf(f[k], w0.y, acc[1]);
+                acc[2] = fmaf(f[k], w0.z, acc[2]); acc[3] = fmaf(f[k], w0.w, acc[3]);
+                acc[4] = fmaf(f[k], w1.x, acc[4]); acc[5] = fmaf(f[k], w1.y, acc[5]);
+                acc[6] = fmaf(f[k], w1.z, acc[6]); acc[7] = fmaf(f[k], w1.w, acc[7]);
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
+                const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[e] = *(const uint32_t*)&h;
+                lo[e] = *(const uint32_t*)&l;
+              }
+              *(uint4*)(base + (size_t)c8 * 128 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *(uint4*)(base + (size_t)(4 + c8) * 128 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+            float acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = s_hw[32 * 16 + c];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float4 w4 = *(const float4*)&s_hw[k * 4];
+              acc[0] = fmaf(f[k], w4.x, acc[0]);
+              acc[1] = fmaf(f[k], w4.y, acc[1]);
+              acc[2] = fmaf(f[k], w4.z, acc[2]);
+              acc[3] = fmaf(f[k], w4.w, acc[3]);
+            }
+            // k = cell*4 + c -> stage = cell/8, kchunk = (cell%8)/2, element = (cell%2)*4 + c
+            __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 3)) * 2) * 4 + ((cell & 7u) >> 1)) * 128 * 8 +
+                           brow * 8 + (cell & 1u) * 4;
+            uint32_t hi[2], lo[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
+              const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
+              const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
+              const __half2 h = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              hi[e] = *(const uint32_t*)&h;
+              lo[e] = *(const uint32_t*)&l;
+            }
+            *(uint2*)base = make_uint2(hi[0], hi[1]);
+            *(uint2*)(base + (size_t)4 * 128 * 8) = make_uint2(lo[0], lo[1]);
+          }
+        }
+      }
+    }
+    int cur_m = -1;
+    bool real = false;
+    uint32_t q = 0;
+    for (int u = sub; !L.head_ch && u < T * nc; u += TC_EPI_WARPS / 4) {
+      const int m = u / nc, c0 = (u - m * nc) << 4;
+      if (m != cur_m) {
+        cur_m = m;
+        q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
+        const uint32_t within = q % (uint32_t)L.per_board;
+        const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+        real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+      }
+      const long long row = L.row0 + q;
+      uint32_t v[16];
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + c0);
+      tc_ld16(taddr, v);
+      if (L.fold) {                                         // + a_hi * w_lo partial sums
+        uint32_t v2[16];
+        tc_ld16(taddr + (uint32_t)cout, v2);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      } else {
+        tc_ld_wait();
+      }
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+          const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+          f[4 * e + j] = x > 0.0f ? x : neg;
+        }
+      }
+      if (L.out) {
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hi[e] = real ? *(const uint32_t*)&h : 0u;
+            lo[e] = real ? *(const uint32_t*)&l : 0u;
+          }
+          const long long chunk = (c0 >> 3) + kc;
+          __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
+          __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
+          *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      if (L.out_f32 && q < nrows) {
+        constexpr float inv = 1.0f / ACT_SCALE;
+        float4* po = (float4*)(L.out_f32 + row * cout + c0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    dbg_mark(edbg, 2, dn);                               // tile(s) drained
+    if (lane == 0) {
+      if (REMOTE) mbar_arrive_remote(&B->t_empty[tb], 0);   // the leader CTA's barrier (cta_group::2)
+      else mbar_arrive(&B->t_empty[tb]);
+    }
+    if (++tb == nbuf) { tb = 0; tph ^= 1; }
+  }
 }
 
 // ------------------------------------------------------------------ the conv kernel
@@ -121,12 +336,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
   const uint32_t tmem = B->tmem_base;
 
   if (warp == 0) {
-    // ===================== producer: bulk copies HBM -> SMEM =====================
+    // ===================== A producer: activation slabs HBM -> SMEM =====================
     // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
-    int ab = 0, aph = 0, ws = 0, wph = 0, dn = 0;
+    int ab = 0, aph = 0, dn = 0;
     for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
       const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
-      const __half* wsrc = L.wpk;
       for (int s = 0; s < nslabs; ++s) {
         const bool is_res = s >= main_slabs;
         const __half* X = is_res ? L.res : L.src;
@@ -147,17 +361,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
         }
         __syncwarp();
         if (++ab == 2) { ab = 0; aph ^= 1; }
-        const int ntap = is_res ? 1 : L.ntaps;
-        for (int t = 0; t < ntap; ++t) {
-          mbar_wait(&B->w_empty[ws], wph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&B->w_full[ws], stage_bytes);
-            bulk_g2s(w_buf + ws * TC_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
-          }
-          __syncwarp();
-          wsrc += stage_bytes / 2;
-          if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == TC_W_WARP) {
+    // ===================== W producer: weight stages L2 -> SMEM =====================
+    int ws = 0, wph = 0;
+    const int nstage = main_slabs * L.ntaps + res_slabs;
+    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
+      const __half* wsrc = L.wpk;
+      for (int t = 0; t < nstage; ++t) {
+        mbar_wait(&B->w_empty[ws], wph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&B->w_full[ws], stage_bytes);
+          bulk_g2s(w_buf + ws * TC_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
         }
+        __syncwarp();
+        wsrc += stage_bytes / 2;
+        if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -243,205 +463,286 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
       if (++tb == nbuf) { tb = 0; tph ^= 1; }
     }
   } else {
-    // ===================== epilogue: TMEM -> bias / ELU / hi-lo split -> HBM =====================
-    // Four warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); the
-    // (M tile, 16-column) units of a group are dealt round-robin to them.  All arithmetic is
-    // on values pre-scaled by ACT_SCALE.
-    const int quad = warp & 3;
-    const int sub = (warp - 2) >> 2;
-    const int nc = cout >> 4;                               // 16-column units per tile
-    int tb = 0, tph = 0, dn = 0;
-    unsigned long long* edbg = (warp == 2 && lane == 0) ? L.dbg : nullptr;
-    const uint32_t nrows = (uint32_t)L.nrows;
-    constexpr float K_ACC = OUT_SCALE * ACT_SCALE;          // accumulator -> scaled activation
-    constexpr float K_L2E = 1.4426950408889634f / ACT_SCALE;
-    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-      mbar_wait(&B->t_full[tb], tph);
-      tc_fence_after();
-      dbg_mark(edbg, 2, dn);                               // accumulators ready
-      if (L.head_ch) {
-        // head layers (cout = 32): a warp takes whole rows of one M tile, so the 1x1 head conv
-        // sees all 32 channels of its position.
-        for (int m = sub; m < T; m += TC_EPI_WARPS / 4) {
-          const uint32_t q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
-          const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
-          const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
-          const bool real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
-          float f[32];
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + h2 * 16);
-            tc_ld16(taddr, v);
-            if (L.fold) {
-              uint32_t v2[16];
-              tc_ld16(taddr + (uint32_t)cout, v2);
-              tc_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-            } else {
-              tc_ld_wait();
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 b4 = *(const float4*)&s_bias[h2 * 16 + 4 * e];
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
-                const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
-                f[h2 * 16 + 4 * e + j] = x > 0.0f ? x : neg;       // ACT_SCALE * activation
-              }
-            }
-          }
-          if (real) {
-            const uint32_t cell = rr * (uint32_t)L.S + cc;
-            const uint32_t mt = board >> 7, brow = board & 127u;
-            if (L.head_ch == 16) {
-              float acc[16];
-#pragma unroll
-              for (int c = 0; c < 16; ++c) acc[c] = s_hw[32 * 16 + c];
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  const float4 w4 = *(const float4*)&s_hw[k * 16 + 4 * c4];
-                  acc[4 * c4 + 0] = fmaf(f[k], w4.x, acc[4 * c4 + 0]);
-                  acc[4 * c4 + 1] = fmaf(f[k], w4.y, acc[4 * c4 + 1]);
-                  acc[4 * c4 + 2] = fmaf(f[k], w4.z, acc[4 * c4 + 2]);
-                  acc[4 * c4 + 3] = fmaf(f[k], w4.w, acc[4 * c4 + 3]);
-                }
-              }
-              // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8
-              __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
-#pragma unroll
-              for (int c8 = 0; c8 < 2; ++c8) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a0 = acc[c8 * 8 + 2 * e], a1 = acc[c8 * 8 + 2 * e + 1];
-                  const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                  const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                  const __half2 h = __floats2half2_rn(x0, x1);
-                  const float2 hf = __half22float2(h);
-                  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                  hi[e] = *(const uint32_t*)&h;
-                  lo[e] = *(const uint32_t*)&l;
-                }
-                *(uint4*)(base + (size_t)c8 * 128 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *(uint4*)(base + (size_t)(4 + c8) * 128 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
-            } else {
-              float acc[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[c] = s_hw[32 * 16 + c];
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const float4 w4 = *(const float4*)&s_hw[k * 4];
-                acc[0] = fmaf(f[k], w4.x, acc[0]);
-                acc[1] = fmaf(f[k], w4.y, acc[1]);
-                acc[2] = fmaf(f[k], w4.z, acc[2]);
-                acc[3] = fmaf(f[k], w4.w, acc[3]);
-              }
-              // k = cell*4 + c -> stage = cell/8, kchunk = (cell%8)/2, element = (cell%2)*4 + c
-              __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 3)) * 2) * 4 + ((cell & 7u) >> 1)) * 128 * 8 +
-                             brow * 8 + (cell & 1u) * 4;
-              uint32_t hi[2], lo[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
-                const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                const __half2 h = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                hi[e] = *(const uint32_t*)&h;
-                lo[e] = *(const uint32_t*)&l;
-              }
-              *(uint2*)base = make_uint2(hi[0], hi[1]);
-              *(uint2*)(base + (size_t)4 * 128 * 8) = make_uint2(lo[0], lo[1]);
-            }
-          }
-        }
-      }
-      int cur_m = -1;
-      bool real = false;
-      uint32_t q = 0;
-      for (int u = sub; !L.head_ch && u < T * nc; u += TC_EPI_WARPS / 4) {
-        const int m = u / nc, c0 = (u - m * nc) << 4;
-        if (m != cur_m) {
-          cur_m = m;
-          q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
-          const uint32_t within = q % (uint32_t)L.per_board;
-          const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
-          real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
-        }
-        const long long row = L.row0 + q;
-        uint32_t v[16];
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + c0);
-        tc_ld16(taddr, v);
-        if (L.fold) {                                         // + a_hi * w_lo partial sums
-          uint32_t v2[16];
-          tc_ld16(taddr + (uint32_t)cout, v2);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        } else {
-          tc_ld_wait();
-        }
-        float f[16];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
-            const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
-            f[4 * e + j] = x > 0.0f ? x : neg;
-          }
-        }
-        if (L.out) {
-#pragma unroll
-          for (int kc = 0; kc < 2; ++kc) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
-              const __half2 h = __floats2half2_rn(x0, x1);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-              hi[e] = real ? *(const uint32_t*)&h : 0u;
-              lo[e] = real ? *(const uint32_t*)&l : 0u;
-            }
-            const long long chunk = (c0 >> 3) + kc;
-            __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
-            __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
-            *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-        if (L.out_f32 && q < nrows) {
-          constexpr float inv = 1.0f / ACT_SCALE;
-          float4* po = (float4*)(L.out_f32 + row * cout + c0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      dbg_mark(edbg, 2, dn);                               // tile(s) drained
-      if (lane == 0) mbar_arrive(&B->t_empty[tb]);
-      if (++tb == nbuf) { tb = 0; tph ^= 1; }
-    }
+    tc_epilogue<T, false>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, blockIdx.x, L.ngroups, gridDim.x);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------ the CTA-pair conv kernel
+// Same computation as k_tc_conv on a pair of SMs (cluster of 2, tcgen05 cta_group::2): one
+// tcgen05.mma covers M = 256 -- the T tiles of this CTA and the T tiles of its peer -- while the
+// B operand (weights) is split along N between the two CTAs' shared memories.  Per SM that
+//   * halves the weight bytes staged from L2 and read by the tensor core (an N = 128 SS-MMA
+//     otherwise needs A 4 KB + B 4 KB per 64 cycles = all 128 B/clk of shared memory),
+//   * lets a weight stage serve 2T tiles while each CTA's TMEM holds only T (double-buffered).
+// Only the leader CTA (cluster rank 0) issues MMAs.  Data arrival in the peer is relayed to the
+// leader's "full" barriers by the peer's otherwise idle warp 1 (mapa + remote mbarrier.arrive);
+// MMA completion is multicast to both CTAs' "empty" / "accumulator ready" barriers
+// (tcgen05.commit ... multicast::cluster); the peer's epilogue warps report "TMEM drained" on the
+// leader's barrier.
+//
+// Weight stage per CTA [kchunk 4][X rows | S rows][8]:
+//   fold (cout <= 64): X = cout rows (leader: w_hi, peer: w_lo)  -> a_hi * [w_hi | w_lo], N = 2 cout
+//                      S = cout/2 rows (leader: w_hi[0:cout/2], peer: w_hi[cout/2:]) -> a_lo * w_hi
+//   else             : X = cout/2 rows of w_hi, S = cout/2 rows of w_lo (this CTA's half of N)
+template <int T>
+struct TCfg2 {
+  static constexpr int NSLAB = T >= 4 ? 2 : 4;             // A slab buffers
+  static constexpr int WSTAGES = 8;
+  static constexpr int WSTAGE_MAX = 4 * 128 * 16;          // 8 KB (cout = 128: 64 + 64 rows)
+  static constexpr int SMEM = NSLAB * TCfg<T>::SLAB + WSTAGES * WSTAGE_MAX + 128 * 4 + 256 + (32 * 16 + 16) * 4 + 128;
+};
+
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {   // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+
+template <int T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_conv2(const __grid_constant__ TCLayer L) {
+  using Cfg = TCfg<T>;
+  using Cfg2 = TCfg2<T>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + Cfg2::NSLAB * Cfg::SLAB;
+  float* s_bias = (float*)(w_buf + Cfg2::WSTAGES * Cfg2::WSTAGE_MAX);
+  TCBarriers* B = (TCBarriers*)(s_bias + 128);
+  float* s_hw = (float*)((uint8_t*)B + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cout = L.cout;
+  const bool fold = L.fold != 0;
+  const int cpt = fold ? 2 * cout : cout;                  // TMEM columns per M tile
+  const int nbuf = (T * cpt <= 256) ? 2 : 1;
+  const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
+  const int nslabs = main_slabs + res_slabs;
+  const int xr = fold ? cout : cout / 2, sr = cout / 2;    // rows of the two parts of this CTA's stage
+  const uint32_t stage_bytes = 4u * (uint32_t)(xr + sr) * 16u;
+  // pair-groups: the pair handles groups 2 pg (leader) and 2 pg + 1 (peer); both CTAs run the
+  // same number of iterations (rows past nrows are padding and masked in the epilogue)
+  const int npairs = (L.ngroups + 1) / 2;
+  const int g_first = 2 * (int)(blockIdx.x >> 1) + (int)rank, g_end = 2 * npairs, g_step = (int)gridDim.x;
+
+  if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
+  if (L.head_ch) {
+    for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
+    if (threadIdx.x < L.head_ch) s_hw[32 * 16 + threadIdx.x] = L.head_b[threadIdx.x] * ACT_SCALE;
+  }
+  if (warp == 0 && lane == 0) {
+    const uint32_t full_count = rank == 0 ? 2u : 1u;       // leader: own producer + the peer's relay
+    for (int i = 0; i < Cfg2::NSLAB; ++i) { mbar_init(&B->a_full[i], full_count); mbar_init(&B->a_empty[i], 1); }
+    for (int i = 0; i < Cfg2::WSTAGES; ++i) { mbar_init(&B->w_full[i], full_count); mbar_init(&B->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], 2 * TC_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // the peer's barriers are initialised too
+  tc_fence_after();
+  const uint32_t tmem = B->tmem_base;
+
+  if (warp == 0) {
+    // ===================== A producer (each CTA loads its own slabs) =====================
+    int ab = 0, aph = 0, dn = 0;
+    for (int g = g_first; g < g_end; g += g_step) {
+      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
+      for (int s = 0; s < nslabs; ++s) {
+        const bool is_res = s >= main_slabs;
+        const __half* X = is_res ? L.res : L.src;
+        const int xch = is_res ? L.res_ch : L.src_ch;
+        const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
+        mbar_wait(&B->a_empty[ab], aph ^ 1);
+        if (lane == 0) dbg_mark(L.dbg, 0, dn);
+        if (elect_one()) {
+          mbar_expect_tx(&B->a_full[ab], Cfg::SLAB);
+          uint8_t* dst = a_buf + ab * Cfg::SLAB;
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+            for (int j = 0; j < TC_KS / 8; ++j) {
+              const __half* p = X + ((long long)(hl * (xch / 8) + kc0 + j) * L.plane_rows + r0) * 8;
+              bulk_g2s(dst + (hl * (TC_KS / 8) + j) * Cfg::PLANE, p, Cfg::PLANE, &B->a_full[ab]);
+            }
+        }
+        __syncwarp();
+        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == TC_W_WARP) {
+    // ===================== W producer (each CTA loads its half of every weight stage) =====================
+    int ws = 0, wph = 0, dnw = 0;
+    const int nstage = main_slabs * L.ntaps + res_slabs;
+    for (int g = g_first; g < g_end; g += g_step) {
+      const __half* wsrc = L.wpk + (size_t)rank * (stage_bytes / 2);
+      for (int t = 0; t < nstage; ++t) {
+        mbar_wait(&B->w_empty[ws], wph ^ 1);
+        if (lane == 0) { dbg_mark_cta(L.dbg, 4, dnw, 0); dbg_mark_cta(L.dbg, 6, dnw, 1); }
+        if (elect_one()) {
+          mbar_expect_tx(&B->w_full[ws], stage_bytes);
+          bulk_g2s(w_buf + ws * Cfg2::WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+        }
+        __syncwarp();
+        wsrc += stage_bytes;                               // 2 CTAs x stage_bytes, in halfs
+        if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer relay: "my slab / stage landed" -> the leader's full barriers =====================
+    int ab = 0, aph = 0, ws = 0, wph = 0, dnr = 0;
+    for (int g = g_first; g < g_end; g += g_step) {
+      for (int s = 0; s < nslabs; ++s) {
+        const int ntap = s >= main_slabs ? 1 : L.ntaps;
+        mbar_wait(&B->a_full[ab], aph);
+        if (lane == 0) mbar_arrive_remote(&B->a_full[ab], 0);
+        __syncwarp();
+        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
+        for (int t = 0; t < ntap; ++t) {
+          mbar_wait(&B->w_full[ws], wph);
+          if (lane == 0) { dbg_mark_cta(L.dbg, 5, dnr, 1); mbar_arrive_remote(&B->w_full[ws], 0); }
+          __syncwarp();
+          if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader): M = 256 over both CTAs =====================
+    const uint32_t idesc = instr_desc(256, cout), idesc2 = instr_desc(256, 2 * cout);
+    const uint32_t w_lbo = (uint32_t)(xr + sr) * 16u;
+    constexpr uint64_t A_TILE = 128u * 16u / 16u;
+    constexpr uint64_t A_K16 = 2u * Cfg::PLANE / 16u;
+    constexpr uint64_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;
+    const uint64_t w_k16 = (uint64_t)(2u * w_lbo / 16u);
+    const uint64_t w_s16 = (uint64_t)xr;                    // X -> S part of a stage (16-byte units)
+    const uint64_t ad_base = smem_desc(smem_u32(a_buf) + (uint32_t)TC_HALO * 16u, Cfg::PLANE, 128);
+    const uint64_t bd_base = smem_desc(smem_u32(w_buf), w_lbo, 128);
+    int sh[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
+    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0, dn = 0, dn3 = 0;
+    for (int g = g_first; g < g_end; g += g_step) {
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);
+      mbar_wait_cluster(&B->t_empty[tb], tph ^ 1);
+      tc_fence_after();
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);
+      const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt);
+      for (int s = 0; s < nslabs; ++s) {
+        const bool is_res = s >= main_slabs;
+        const int ntap = is_res ? 1 : L.ntaps;
+        mbar_wait_cluster(&B->a_full[ab], aph);
+        tc_fence_after();
+        if (lane == 0) dbg_mark(L.dbg, 1, dn);
+        const uint64_t ad_slab = ad_base + (uint64_t)(ab * (Cfg::SLAB / 16));
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < ntap) {
+            if (lane == 0) dbg_mark(L.dbg, 3, dn3);
+            mbar_wait_cluster(&B->w_full[ws], wph);
+            tc_fence_after();
+            if (lane == 0) dbg_mark(L.dbg, 3, dn3);
+            const uint64_t ad0 = ad_slab + (uint64_t)(int64_t)(is_res ? 0 : sh[t]);
+            const uint64_t bd0 = bd_base + (uint64_t)(ws * (Cfg2::WSTAGE_MAX / 16));
+            const uint32_t first = (uint32_t)(s | t);
+            const bool last_tap = t == ntap - 1;
+            if (elect_one()) {
+              if (fold) {
+#pragma unroll
+                for (int m = 0; m < T; ++m) {
+#pragma unroll
+                  for (int k = 0; k < TC_KS / 16; ++k)
+                    tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, bd0 + k * w_k16, idesc2, (first | k) != 0);
+#pragma unroll
+                  for (int k = 0; k < TC_KS / 16; ++k)
+                    tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, bd0 + k * w_k16 + w_s16, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int m = 0; m < T; ++m) {
+#pragma unroll
+                  for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
+#pragma unroll
+                    for (int k = 0; k < TC_KS / 16; ++k)
+                      tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0),
+                              bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), idesc, (first | pass | k) != 0);
+                  }
+                }
+              }
+              tc_commit2(&B->w_empty[ws]);
+              if (last_tap) tc_commit2(&B->a_empty[ab]);
+              if (last_tap && s == nslabs - 1) tc_commit2(&B->t_full[tb]);
+            }
+            __syncwarp();
+            if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
+          }
+        }
+        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
+      }
+      if (lane == 0) dbg_mark(L.dbg, 1, dn);
+      if (++tb == nbuf) { tb = 0; tph ^= 1; }
+    }
+  } else {
+    if (rank == 0) tc_epilogue<T, false>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, g_first, g_end, g_step);
+    else tc_epilogue<T, true>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, g_first, g_end, g_step);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // nobody leaves while the peer may still touch its barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// Weights for the CTA-pair kernel: [stage][cta 2][kchunk 4][X rows | S rows][8] (see k_tc_conv2).
+__global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict__ wres, int ntaps, int cin, int rcin,
+                           int cout, int fold, __half* __restrict__ out) {
+  const int main_stages = (cin / TC_KS) * ntaps;
+  const int nstages = main_stages + (wres ? rcin / TC_KS : 0);
+  const int xr = fold ? cout : cout / 2, sr = cout / 2, rows = xr + sr;
+  const long long per_cta = (long long)4 * rows * 8;      // halfs
+  const long long total = (long long)nstages * 2 * per_cta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int stage = (int)(i / (2 * per_cta));
+    const int r = (int)(i % (2 * per_cta));
+    const int cta = r / (int)per_cta, r2 = r % (int)per_cta;
+    const int j = r2 / (rows * 8), row = (r2 / 8) % rows, e = r2 % 8;
+    // which weight row / half this smem row holds
+    int n, lo;
+    if (fold) {
+      if (row < xr) { n = row; lo = cta; }                              // X: leader w_hi, peer w_lo
+      else { n = cta * sr + (row - xr); lo = 0; }                        // S: halves of w_hi
+    } else {
+      if (row < xr) { n = cta * xr + row; lo = 0; }                      // X: this CTA's half of w_hi
+      else { n = cta * sr + (row - xr); lo = 1; }                        // S: this CTA's half of w_lo
+    }
+    const int kin = j * 8 + e;
+    float x;
+    if (stage < main_stages) {
+      const int slab = stage / ntaps, tap = stage % ntaps;
+      x = w[((size_t)tap * cin + slab * TC_KS + kin) * cout + n];
+    } else {
+      const int slab = stage - main_stages;
+      x = wres[(size_t)(slab * TC_KS + kin) * cout + n];
+    }
+    x *= W_SCALE;
+    const __half h = __float2half_rn(x);
+    out[i] = lo ? __float2half_rn(x - __half2float(h)) : h;
   }
 }
 
@@ -597,6 +898,8 @@ static const TcLayerDef kTcLayers[11] = {
 struct a5_tc_state {
   __half* act[11] = {};
   __half* wpk[11] = {};
+  __half* wpk2[11] = {};        // CTA-pair layout
+  int cta2 = 1;                 // use k_tc_conv2 (A5_TC_CTA2=0 selects the single-CTA kernel)
   long long plane_rows = 0;
   int t128 = 4, t64 = 2, fold = 1;
   int num_sms = 0;
@@ -608,7 +911,7 @@ namespace a5 {
 static long long tc_plane_rows(const a5_net* net) {
   PosSpace ps(net->S);
   long long valid = (long long)net->max_batch * ps.per_board;
-  long long padded = (valid + 511) / 512 * 512;          // whole groups for every T
+  long long padded = (valid + 1023) / 1024 * 1024;       // whole pair-groups for every T
   return ps.guard + padded + ps.guard + TC_HALO;
 }
 
@@ -625,15 +928,19 @@ int tc_alloc(a5_net* net) {
     const TcLayerDef& L = kTcLayers[l];
     size_t stages = (size_t)(L.cin / TC_KS) * 9 + (L.res_src >= 0 ? L.res_cin / TC_KS : 0);
     A5_CUDA(cudaMalloc(&tc->wpk[l], stages * 2 * TC_KS * L.cout * sizeof(__half)));
+    A5_CUDA(cudaMalloc(&tc->wpk2[l], stages * 2 * 4 * (L.cout + L.cout / 2) * 8 * sizeof(__half)));
   }
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg2<4>::SMEM));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg2<2>::SMEM));
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
   const char* ev;
   tc->t128 = ((ev = getenv("A5_TC_T128")) && atoi(ev) == 2) ? 2 : 4;
   tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
+  tc->cta2 = ((ev = getenv("A5_TC_CTA2")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
   int dev = 0;
@@ -646,6 +953,7 @@ void tc_free(a5_net* net) {
   if (!net->tc) return;
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->act[i]);
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk[i]);
+  for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk2[i]);
   heads_free(net->tc->heads);
   delete net->tc;
   net->tc = nullptr;
@@ -659,6 +967,8 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     const float* w = (l & 1) ? t[t0 + 2] : t[t0 + 4];
     const float* wres = (l & 1) ? nullptr : t[t0 + 0];
     k_tc_pack<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, tc->wpk[l]);
+    A5_CUDA(cudaGetLastError());
+    k_tc_pack2<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
     A5_CUDA(cudaGetLastError());
   }
   return heads_set_weights(net, tc->heads, t, st);
@@ -705,15 +1015,29 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
-    const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
     L.fold = (D.cout <= 64) ? tc->fold : 0;
-    L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 4 * 256 : nullptr;
-    const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
-    L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows; L.ngroups = ngroups;
+    L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
+    L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
-    int grid = ngroups < tc->num_sms ? ngroups : tc->num_sms;
-    if (T == 4) k_tc_conv<4><<<grid, TC_THREADS, TCfg<4>::SMEM, st>>>(L);
-    else k_tc_conv<2><<<grid, TC_THREADS, TCfg<2>::SMEM, st>>>(L);
+    if (tc->cta2) {
+      // CTA pairs: T tiles per CTA, 2T per weight stage; TMEM double-buffers for every layer
+      const int T = (D.cout == 32) ? 4 : 2;
+      const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
+      const int npairs = (ngroups + 1) / 2;
+      L.ngroups = ngroups;
+      L.wpk = tc->wpk2[l];
+      const int maxpairs = tc->num_sms / 2;
+      const int grid = 2 * (npairs < maxpairs ? npairs : maxpairs);
+      if (T == 4) k_tc_conv2<4><<<grid, TC_THREADS, TCfg2<4>::SMEM, st>>>(L);
+      else k_tc_conv2<2><<<grid, TC_THREADS, TCfg2<2>::SMEM, st>>>(L);
+    } else {
+      const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
+      const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
+      L.ngroups = ngroups;
+      int grid = ngroups < tc->num_sms ? ngroups : tc->num_sms;
+      if (T == 4) k_tc_conv<4><<<grid, TC_THREADS, TCfg<4>::SMEM, st>>>(L);
+      else k_tc_conv<2><<<grid, TC_THREADS, TCfg<2>::SMEM, st>>>(L);
+    }
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
   }
@@ -732,7 +1056,7 @@ int a5_net_tc_available(void) { return 1; }
 int a5__debug_keep_head_acts(int on) { g_tc_keep_head_acts = on != 0; return A5_OK; }
 
 // internal tooling: clock64 timeline of CTA 0 for every conv layer of one forward;
-// d_dbg = uint64 [10][4][256] (zeroed by the caller): roles 0 producer, 1 MMA issuer (groups/slabs),
+// d_dbg = uint64 [10][8][256] (zeroed by the caller): roles 0 producer, 1 MMA issuer (groups/slabs),
 // 2 epilogue warp 2, 3 MMA issuer (weight stages: wait, landed).
 int a5__debug_timeline(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value,
                        unsigned long long* d_dbg, void* stream) {

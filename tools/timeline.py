@@ -16,7 +16,7 @@ net = DeviceNet(S, n, glorot_init(S, 0), mode=_lib.NET_TC)
 planes = torch.from_numpy((np.random.default_rng(0).random((n, 3, S, S)) < 0.2).astype(np.int8)).cuda()
 prob = torch.empty((n, S * S), device="cuda"); val = torch.empty((n,), device="cuda")
 net.forward(planes, prob, val)
-dbg = torch.zeros((10, 4, 256), dtype=torch.int64, device="cuda")
+dbg = torch.zeros((10, 8, 256), dtype=torch.int64, device="cuda")
 check(fn(net.handle, ptr(planes), n, ptr(prob), ptr(val), ptr(dbg), stream_ptr()))
 torch.cuda.synchronize()
 if layer == 0:      # summary: CTA-0 cycles per layer (clock-independent)
@@ -26,21 +26,21 @@ if layer == 0:      # summary: CTA-0 cycles per layer (clock-independent)
         nz = dl[dl > 0]
         span = int(nz.max() - nz.min())
         tot += span
-        print(f"layer {l+1:2d}: {span:9d} cycles")
-    print(f"sum      : {tot:9d} cycles = {tot/1.965e3:.0f} us at 1965 MHz")
+        print(f"layer {l+1:2d}: {span:9d} ns")
+    print(f"sum      : {tot:9d} ns")
     sys.exit(0)
 d = dbg.cpu().numpy()[layer - 1]
 t0 = min(x for x in d.ravel() if x > 0)
 ev = []
 names = {0: "P slab-issue", 1: "M", 2: "E"}
-for role in range(4):
+for role in range(8):
     for i, x in enumerate(d[role]):
         if x > 0:
             ev.append((int(x - t0), role, i))
 ev.sort()
 nslab = {1: 1, 2: 3, 3: 2, 4: 6, 5: 4, 6: 5, 7: 4, 8: 6, 9: 2, 10: 3}[layer]
 per_group_m = 3 + nslab
-for t, role, i in ev[: ngr * (per_group_m + 2 + nslab + 18 * nslab)]:
+for t, role, i in ev[: ngr * (per_group_m + 2 + nslab + 48 * nslab)]:
     if role == 1:
         k = i % per_group_m
         what = ["wait-tmem", "tmem-free"][k] if k < 2 else ("issued-all" if k == per_group_m - 1 else f"slab{k-2}-landed")
@@ -49,5 +49,11 @@ for t, role, i in ev[: ngr * (per_group_m + 2 + nslab + 18 * nslab)]:
         print(f"{t:9d}  PRODUCER slab {i} issue")
     elif role == 2:
         print(f"{t:9d}  EPI g{i // 2} {'ready' if i % 2 == 0 else 'drained'}")
-    else:
+    elif role == 3:
         print(f"{t:9d}      stage {i // 2} {'wait' if i % 2 == 0 else 'landed'}")
+    elif role == 4:
+        print(f"{t:9d}          W-leader issue stage {i}")
+    elif role == 5:
+        print(f"{t:9d}          RELAY stage {i} landed in peer")
+    elif role == 6:
+        print(f"{t:9d}          W-peer issue stage {i}")
