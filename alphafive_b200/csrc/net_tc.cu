@@ -51,6 +51,7 @@ struct TCLayer {
   const __half* wpk;
   const float* bias;
   __half* out;
+  __half* out2; int split;       // merged layers: channels [0, split) -> out, [split, cout) -> out2
   float* out_f32;
   int cout, ntaps;
   int fold;                      // 1: hi*[Whi|Wlo] as one N = 2*cout MMA (cout <= 64)
@@ -90,6 +91,12 @@ __device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int role, int&
 __device__ __forceinline__ void dbg_mark_cta(unsigned long long* dbg, int role, int& n, int cta) {
   if (dbg && (int)blockIdx.x == cta && n < 256) dbg[role * 256 + n++] = dbg_now();
 }
+
+// Programmatic dependent launch: every conv kernel lets its successor be scheduled at once (its CTAs
+// take over SMs as this grid's CTAs exit and run their prologue -- barrier init, TMEM alloc, weight
+// prefetch -- behind this grid's tail); only the activation producer must wait for the predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------ epilogue (shared by both conv kernels)
 // TMEM -> bias / ELU / hi-lo split -> HBM for the groups g_first, g_first + g_step, ... < g_end of
@@ -269,9 +276,12 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
             hi[e] = real ? *(const uint32_t*)&h : 0u;
             lo[e] = real ? *(const uint32_t*)&l : 0u;
           }
-          const long long chunk = (c0 >> 3) + kc;
-          __half* ph = L.out + (chunk * L.plane_rows + row) * 8;
-          __half* pl = L.out + (((long long)(cout >> 3) + chunk) * L.plane_rows + row) * 8;
+          const bool second = L.out2 && c0 >= L.split;
+          __half* ob = second ? L.out2 : L.out;
+          const int och = L.out2 ? (second ? cout - L.split : L.split) : cout;
+          const long long chunk = ((second ? c0 - L.split : c0) >> 3) + kc;
+          __half* ph = ob + (chunk * L.plane_rows + row) * 8;
+          __half* pl = ob + (((long long)(och >> 3) + chunk) * L.plane_rows + row) * 8;
           *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -315,6 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
   const int nslabs = main_slabs + res_slabs;
   const uint32_t stage_bytes = 2u * (TC_KS / 8) * cout * 16u;
 
+  pdl_launch_dependents();
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (L.head_ch) {
     for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
     // ===================== A producer: activation slabs HBM -> SMEM =====================
     // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
     int ab = 0, aph = 0, dn = 0;
+    pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
       const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
       for (int s = 0; s < nslabs; ++s) {
@@ -536,6 +548,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
   const int npairs = (L.ngroups + 1) / 2;
   const int g_first = 2 * (int)(blockIdx.x >> 1) + (int)rank, g_end = 2 * npairs, g_step = (int)gridDim.x;
 
+  pdl_launch_dependents();
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (L.head_ch) {
     for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
@@ -561,6 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
   if (warp == 0) {
     // ===================== A producer (each CTA loads its own slabs) =====================
     int ab = 0, aph = 0, dn = 0;
+    pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = g_first; g < g_end; g += g_step) {
       const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
       for (int s = 0; s < nslabs; ++s) {
@@ -710,8 +724,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
 }
 
 // Weights for the CTA-pair kernel: [stage][cta 2][kchunk 4][X rows | S rows][8] (see k_tc_conv2).
-__global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict__ wres, int ntaps, int cin, int rcin,
-                           int cout, int fold, __half* __restrict__ out) {
+// `wb` (optional): a second kernel over the same input whose output channels follow the `na` of `w`
+// (two convs of one tensor merged into one layer).
+__global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict__ wb, int na, const float* __restrict__ wres,
+                           int ntaps, int cin, int rcin, int cout, int fold, __half* __restrict__ out) {
   const int main_stages = (cin / TC_KS) * ntaps;
   const int nstages = main_stages + (wres ? rcin / TC_KS : 0);
   const int xr = fold ? cout : cout / 2, sr = cout / 2, rows = xr + sr;
@@ -735,7 +751,8 @@ __global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict_
     float x;
     if (stage < main_stages) {
       const int slab = stage / ntaps, tap = stage % ntaps;
-      x = w[((size_t)tap * cin + slab * TC_KS + kin) * cout + n];
+      const size_t kk = (size_t)tap * cin + slab * TC_KS + kin;
+      x = !wb ? w[kk * cout + n] : (n < na ? w[kk * na + n] : wb[kk * (cout - na) + (n - na)]);
     } else {
       const int slab = stage - main_stages;
       x = wres[(size_t)(slab * TC_KS + kin) * cout + n];
@@ -899,7 +916,14 @@ struct a5_tc_state {
   __half* act[11] = {};
   __half* wpk[11] = {};
   __half* wpk2[11] = {};        // CTA-pair layout
+  // block3-conv1 and block4-conv1 both read block2's output (network.py:68,79): the CTA-pair path
+  // runs them as ONE layer of cout = 32 + 64 (N = 96 MMAs instead of N = 32/64 ones below the
+  // ~44-cycle MMA floor, and the 128-channel input is read once)
+  __half* wpk2_m = nullptr;
+  float* bias_m = nullptr;
   int cta2 = 1;                 // use k_tc_conv2 (A5_TC_CTA2=0 selects the single-CTA kernel)
+  int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
+  int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
   int t128 = 4, t64 = 2, fold = 1;
   int num_sms = 0;
@@ -907,6 +931,22 @@ struct a5_tc_state {
 };
 
 namespace a5 {
+
+// launch with the programmatic-stream-serialization attribute (see pdl_wait)
+template <typename K>
+static cudaError_t launch_pdl(K kernel, int grid, int threads, size_t smem, cudaStream_t st, const TCLayer& L, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, L);
+}
 
 static long long tc_plane_rows(const a5_net* net) {
   PosSpace ps(net->S);
@@ -930,6 +970,8 @@ int tc_alloc(a5_net* net) {
     A5_CUDA(cudaMalloc(&tc->wpk[l], stages * 2 * TC_KS * L.cout * sizeof(__half)));
     A5_CUDA(cudaMalloc(&tc->wpk2[l], stages * 2 * 4 * (L.cout + L.cout / 2) * 8 * sizeof(__half)));
   }
+  A5_CUDA(cudaMalloc(&tc->wpk2_m, (size_t)(128 / TC_KS) * 9 * 2 * 4 * 96 * 8 * sizeof(__half)));
+  A5_CUDA(cudaMalloc(&tc->bias_m, 96 * sizeof(float)));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
@@ -941,6 +983,8 @@ int tc_alloc(a5_net* net) {
   tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
   tc->cta2 = ((ev = getenv("A5_TC_CTA2")) && atoi(ev) == 0) ? 0 : 1;
+  tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
+  tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
   int dev = 0;
@@ -954,6 +998,8 @@ void tc_free(a5_net* net) {
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->act[i]);
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk[i]);
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk2[i]);
+  cudaFree(net->tc->wpk2_m);
+  cudaFree(net->tc->bias_m);
   heads_free(net->tc->heads);
   delete net->tc;
   net->tc = nullptr;
@@ -968,9 +1014,13 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     const float* wres = (l & 1) ? nullptr : t[t0 + 0];
     k_tc_pack<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, tc->wpk[l]);
     A5_CUDA(cudaGetLastError());
-    k_tc_pack2<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
+    k_tc_pack2<<<256, 256, 0, st>>>(w, nullptr, 0, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
     A5_CUDA(cudaGetLastError());
   }
+  k_tc_pack2<<<256, 256, 0, st>>>(t[T_B3_C1_K], t[T_B4_C1_K], 32, nullptr, 9, 128, 0, 96, 0, tc->wpk2_m);
+  A5_CUDA(cudaGetLastError());
+  A5_CUDA(cudaMemcpyAsync(tc->bias_m, net->bias[5], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  A5_CUDA(cudaMemcpyAsync(tc->bias_m + 32, net->bias[7], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return heads_set_weights(net, tc->heads, t, st);
 }
 
@@ -993,9 +1043,12 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
   for (int l = 1; l <= 10; ++l) {
-    const TcLayerDef& D = kTcLayers[l];
+    TcLayerDef D = kTcLayers[l];
     TCLayer L;
     memset(&L, 0, sizeof(L));
+    const bool merged = tc->cta2 && tc->merge && l == 5;      // block3-conv1 + block4-conv1 as one cout = 96 layer
+    if (tc->cta2 && tc->merge && l == 7) { TC_MARK(1 + l); continue; }
+    if (merged) D.cout = 96;
     L.src = tc->act[D.src]; L.src_ch = D.cin;
     L.res = D.res_src >= 0 ? tc->act[D.res_src] : nullptr; L.res_ch = D.res_cin;
     L.wpk = tc->wpk[l];
@@ -1011,6 +1064,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
       L.head_out = l == 6 ? io.a_val : io.a_pol;
       L.head_nst = l == 6 ? io.nst_val : io.nst_pol;
     }
+    if (merged) { L.bias = tc->bias_m; L.out2 = tc->act[B4H]; L.split = 32; }
     L.cout = D.cout; L.ntaps = 9;
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
@@ -1025,18 +1079,18 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
       const int npairs = (ngroups + 1) / 2;
       L.ngroups = ngroups;
-      L.wpk = tc->wpk2[l];
+      L.wpk = merged ? tc->wpk2_m : tc->wpk2[l];
       const int maxpairs = tc->num_sms / 2;
       const int grid = 2 * (npairs < maxpairs ? npairs : maxpairs);
-      if (T == 4) k_tc_conv2<4><<<grid, TC_THREADS, TCfg2<4>::SMEM, st>>>(L);
-      else k_tc_conv2<2><<<grid, TC_THREADS, TCfg2<2>::SMEM, st>>>(L);
+      if (T == 4) A5_CUDA(launch_pdl(k_tc_conv2<4>, grid, TC_THREADS, TCfg2<4>::SMEM, st, L, tc->pdl));
+      else A5_CUDA(launch_pdl(k_tc_conv2<2>, grid, TC_THREADS, TCfg2<2>::SMEM, st, L, tc->pdl));
     } else {
       const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
       L.ngroups = ngroups;
       int grid = ngroups < tc->num_sms ? ngroups : tc->num_sms;
-      if (T == 4) k_tc_conv<4><<<grid, TC_THREADS, TCfg<4>::SMEM, st>>>(L);
-      else k_tc_conv<2><<<grid, TC_THREADS, TCfg<2>::SMEM, st>>>(L);
+      if (T == 4) A5_CUDA(launch_pdl(k_tc_conv<4>, grid, TC_THREADS, TCfg<4>::SMEM, st, L, tc->pdl));
+      else A5_CUDA(launch_pdl(k_tc_conv<2>, grid, TC_THREADS, TCfg<2>::SMEM, st, L, tc->pdl));
     }
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
