@@ -55,6 +55,7 @@ struct TCLayer {
   float* out_f32;
   int cout, ntaps;
   int fold;                      // 1: hi*[Whi|Wlo] as one N = 2*cout MMA (cout <= 64)
+  int nslab_buf, w_bytes;        // pair kernel: A slab buffers, bytes of the weight region (ring or resident set)
   unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
   // fused 1x1 head conv + ELU in the epilogue (network.py:69-70 value, :81-82 policy): the
   // layer's own activation is then not stored; the head output goes out as the A operand of
@@ -502,13 +503,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
 //   fold (cout <= 64): X = cout rows (leader: w_hi, peer: w_lo)  -> a_hi * [w_hi | w_lo], N = 2 cout
 //                      S = cout/2 rows (leader: w_hi[0:cout/2], peer: w_hi[cout/2:]) -> a_lo * w_hi
 //   else             : X = cout/2 rows of w_hi, S = cout/2 rows of w_lo (this CTA's half of N)
-template <int T>
-struct TCfg2 {
-  static constexpr int NSLAB = T >= 4 ? 2 : 4;             // A slab buffers
-  static constexpr int WSTAGES = 8;
-  static constexpr int WSTAGE_MAX = 4 * 128 * 16;          // 8 KB (cout = 128: 64 + 64 rows)
-  static constexpr int SMEM = NSLAB * TCfg<T>::SLAB + WSTAGES * WSTAGE_MAX + 128 * 4 + 256 + (32 * 16 + 16) * 4 + 128;
-};
+//
+// Issue side (measured, tools/micro/mma_bench7/8.cu): one thread issues a tcgen05.mma every ~50 cycles
+// and the tensor core needs >= ~40 cycles per instruction (the 4 KB A operand at 128 B/clk), so with
+// N <= 128 a single issuer that also polls a weight barrier and commits per (slab, tap) stage cannot
+// keep the pipe fed.  Hence (i) TWO issuer warps, each owning half of the CTA's M tiles (separate
+// accumulators: no ordering between them is needed; every "empty"/"ready" barrier counts both
+// commits), and (ii) RESW: when the layer's whole weight set fits beside the slabs it is loaded once
+// per CTA and stays resident -- no per-stage wait / commit, and 1/16 of the L2 -> SMEM weight traffic.
+constexpr int TC2_THREADS = TC_THREADS + 32;
+constexpr int TC2_MMA_WARP1 = TC_W_WARP + 1;              // second MMA issuer (leader CTA only)
+constexpr int TC2_WSTAGES = 8;
+constexpr int TC2_WSTAGE_MAX = 4 * 128 * 16;              // 8 KB (cout = 128: 64 + 64 rows)
+constexpr int TC2_MISC = 128 * 4 + 256 + (32 * 16 + 16) * 4 + 128;
+constexpr int TC2_SMEM_LIMIT = 232448;                    // 227 KB opt-in maximum per CTA
 
 __device__ __forceinline__ void tc_commit2(uint64_t* bar) {   // arrive on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -522,14 +530,38 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 
-template <int T>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_conv2(const __grid_constant__ TCLayer L) {
-  using Cfg = TCfg<T>;
-  using Cfg2 = TCfg2<T>;
+// slab geometry of the pair kernel: the halo is a template parameter (>= pitch + 1, multiple of 8: 16 for
+// boards up to 14x14, 24 for 15x15) -- the 2 KB per slab it saves at 11x11 buy a third slab buffer
+// beside the resident weights of block1-conv2
+template <int T, int HALO>
+struct TCfgH {
+  static constexpr int ROWS = T * 128;
+  static constexpr int SROWS = ROWS + 2 * HALO;
+  static constexpr int PLANE = SROWS * 16;
+  static constexpr int SLAB = 2 * (TC_KS / 8) * PLANE;
+};
+
+// Descriptors as (lo, hi) words: only the 14-bit start-address field in the low word changes between
+// MMAs, so the issuer's address arithmetic is 32-bit and the high words stay loop-invariant.
+__device__ __forceinline__ void tc_mma2s(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+}
+
+template <int T, bool RESW, int HALO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc_conv2(const __grid_constant__ TCLayer L) {
+  using Cfg = TCfgH<T, HALO>;
   extern __shared__ __align__(128) uint8_t smem[];
+  const int nsb = L.nslab_buf;                             // A slab buffers (2..4)
   uint8_t* a_buf = smem;
-  uint8_t* w_buf = smem + Cfg2::NSLAB * Cfg::SLAB;
-  float* s_bias = (float*)(w_buf + Cfg2::WSTAGES * Cfg2::WSTAGE_MAX);
+  uint8_t* w_buf = smem + nsb * Cfg::SLAB;
+  float* s_bias = (float*)(w_buf + L.w_bytes);
   TCBarriers* B = (TCBarriers*)(s_bias + 128);
   float* s_hw = (float*)((uint8_t*)B + 256);
 
@@ -541,6 +573,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
   const int nbuf = (T * cpt <= 256) ? 2 : 1;
   const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
   const int nslabs = main_slabs + res_slabs;
+  const int nstage = main_slabs * L.ntaps + res_slabs;
   const int xr = fold ? cout : cout / 2, sr = cout / 2;    // rows of the two parts of this CTA's stage
   const uint32_t stage_bytes = 4u * (uint32_t)(xr + sr) * 16u;
   // pair-groups: the pair handles groups 2 pg (leader) and 2 pg + 1 (peer); both CTAs run the
@@ -551,14 +584,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
   pdl_launch_dependents();
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (L.head_ch) {
-    for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
+    for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC2_THREADS) s_hw[i] = L.head_w[i];
     if (threadIdx.x < L.head_ch) s_hw[32 * 16 + threadIdx.x] = L.head_b[threadIdx.x] * ACT_SCALE;
   }
   if (warp == 0 && lane == 0) {
     const uint32_t full_count = rank == 0 ? 2u : 1u;       // leader: own producer + the peer's relay
-    for (int i = 0; i < Cfg2::NSLAB; ++i) { mbar_init(&B->a_full[i], full_count); mbar_init(&B->a_empty[i], 1); }
-    for (int i = 0; i < Cfg2::WSTAGES; ++i) { mbar_init(&B->w_full[i], full_count); mbar_init(&B->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], 2 * TC_EPI_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&B->a_full[i], full_count); mbar_init(&B->a_empty[i], 2); }
+    for (int i = 0; i < TC2_WSTAGES; ++i) { mbar_init(&B->w_full[i], full_count); mbar_init(&B->w_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 2); mbar_init(&B->t_empty[i], 2 * TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -576,7 +609,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
     int ab = 0, aph = 0, dn = 0;
     pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = g_first; g < g_end; g += g_step) {
-      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
+      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - HALO;
       for (int s = 0; s < nslabs; ++s) {
         const bool is_res = s >= main_slabs;
         const __half* X = is_res ? L.res : L.src;
@@ -596,121 +629,145 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
             }
         }
         __syncwarp();
-        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
+        if (++ab == nsb) { ab = 0; aph ^= 1; }
       }
     }
   } else if (warp == TC_W_WARP) {
     // ===================== W producer (each CTA loads its half of every weight stage) =====================
-    int ws = 0, wph = 0, dnw = 0;
-    const int nstage = main_slabs * L.ntaps + res_slabs;
-    for (int g = g_first; g < g_end; g += g_step) {
-      const __half* wsrc = L.wpk + (size_t)rank * (stage_bytes / 2);
-      for (int t = 0; t < nstage; ++t) {
-        mbar_wait(&B->w_empty[ws], wph ^ 1);
-        if (lane == 0) { dbg_mark_cta(L.dbg, 4, dnw, 0); dbg_mark_cta(L.dbg, 6, dnw, 1); }
-        if (elect_one()) {
-          mbar_expect_tx(&B->w_full[ws], stage_bytes);
-          bulk_g2s(w_buf + ws * Cfg2::WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+    const __half* wsrc0 = L.wpk + (size_t)rank * (stage_bytes / 2);
+    if (RESW) {
+      if (elect_one()) {
+        mbar_expect_tx(&B->w_full[0], (uint32_t)nstage * stage_bytes);
+        for (int t = 0; t < nstage; ++t)
+          bulk_g2s(w_buf + (size_t)t * stage_bytes, wsrc0 + (size_t)t * stage_bytes, stage_bytes, &B->w_full[0]);
+      }
+      __syncwarp();
+    } else {
+      int ws = 0, wph = 0;
+      for (int g = g_first; g < g_end; g += g_step) {
+        const __half* wsrc = wsrc0;
+        for (int t = 0; t < nstage; ++t) {
+          mbar_wait(&B->w_empty[ws], wph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&B->w_full[ws], stage_bytes);
+            bulk_g2s(w_buf + ws * TC2_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+          }
+          __syncwarp();
+          wsrc += stage_bytes;                             // 2 CTAs x stage_bytes, in halfs
+          if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
         }
-        __syncwarp();
-        wsrc += stage_bytes;                               // 2 CTAs x stage_bytes, in halfs
-        if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
       }
     }
   } else if (warp == 1 && rank != 0) {
     // ===================== peer relay: "my slab / stage landed" -> the leader's full barriers =====================
-    int ab = 0, aph = 0, ws = 0, wph = 0, dnr = 0;
+    int ab = 0, aph = 0, ws = 0, wph = 0;
+    if (RESW) {
+      mbar_wait(&B->w_full[0], 0);
+      if (lane == 0) mbar_arrive_remote(&B->w_full[0], 0);
+      __syncwarp();
+    }
     for (int g = g_first; g < g_end; g += g_step) {
       for (int s = 0; s < nslabs; ++s) {
         const int ntap = s >= main_slabs ? 1 : L.ntaps;
         mbar_wait(&B->a_full[ab], aph);
         if (lane == 0) mbar_arrive_remote(&B->a_full[ab], 0);
         __syncwarp();
-        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
-        for (int t = 0; t < ntap; ++t) {
-          mbar_wait(&B->w_full[ws], wph);
-          if (lane == 0) { dbg_mark_cta(L.dbg, 5, dnr, 1); mbar_arrive_remote(&B->w_full[ws], 0); }
-          __syncwarp();
-          if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
+        if (++ab == nsb) { ab = 0; aph ^= 1; }
+        if (!RESW) {
+          for (int t = 0; t < ntap; ++t) {
+            mbar_wait(&B->w_full[ws], wph);
+            if (lane == 0) mbar_arrive_remote(&B->w_full[ws], 0);
+            __syncwarp();
+            if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
+          }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader): M = 256 over both CTAs =====================
+  } else if ((warp == 1 || warp == TC2_MMA_WARP1) && rank == 0) {
+    // ===================== MMA issuers (leader): M = 256 over both CTAs, T/2 tiles each =====================
+    const int m0 = (warp == 1) ? 0 : T / 2;
+    unsigned long long* dbg = (warp == 1) ? L.dbg : nullptr;
     const uint32_t idesc = instr_desc(256, cout), idesc2 = instr_desc(256, 2 * cout);
     const uint32_t w_lbo = (uint32_t)(xr + sr) * 16u;
-    constexpr uint64_t A_TILE = 128u * 16u / 16u;
-    constexpr uint64_t A_K16 = 2u * Cfg::PLANE / 16u;
-    constexpr uint64_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;
-    const uint64_t w_k16 = (uint64_t)(2u * w_lbo / 16u);
-    const uint64_t w_s16 = (uint64_t)xr;                    // X -> S part of a stage (16-byte units)
-    const uint64_t ad_base = smem_desc(smem_u32(a_buf) + (uint32_t)TC_HALO * 16u, Cfg::PLANE, 128);
-    const uint64_t bd_base = smem_desc(smem_u32(w_buf), w_lbo, 128);
+    // descriptor low-word deltas (the start-address field counts 16-byte units)
+    constexpr uint32_t A_TILE = 128u * 16u / 16u;
+    constexpr uint32_t A_K16 = 2u * Cfg::PLANE / 16u;
+    constexpr uint32_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;
+    const uint32_t w_k16 = 2u * w_lbo / 16u;
+    const uint32_t w_s16 = (uint32_t)xr;                    // X -> S part of a stage (16-byte units)
+    const uint64_t ad64 = smem_desc(smem_u32(a_buf) + (uint32_t)HALO * 16u, Cfg::PLANE, 128);
+    const uint64_t bd64 = smem_desc(smem_u32(w_buf), w_lbo, 128);
+    const uint32_t a_hi = (uint32_t)(ad64 >> 32), b_hi = (uint32_t)(bd64 >> 32);
+    const uint32_t ad_base = (uint32_t)ad64 + (uint32_t)m0 * A_TILE, bd_base = (uint32_t)bd64;
+    const uint32_t w_step = RESW ? stage_bytes / 16u : (uint32_t)(TC2_WSTAGE_MAX / 16);
     int sh[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
-    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0, dn = 0, dn3 = 0;
+    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0, dn = 0;
+    if (RESW) { mbar_wait_cluster(&B->w_full[0], 0); tc_fence_after(); }
     for (int g = g_first; g < g_end; g += g_step) {
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);
+      if (lane == 0) dbg_mark(dbg, 1, dn);
       mbar_wait_cluster(&B->t_empty[tb], tph ^ 1);
       tc_fence_after();
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);
-      const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt);
+      if (lane == 0) dbg_mark(dbg, 1, dn);
+      const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt + m0 * cpt);
+      uint32_t bd = bd_base;                                // RESW: walks through the resident stages
       for (int s = 0; s < nslabs; ++s) {
         const bool is_res = s >= main_slabs;
         const int ntap = is_res ? 1 : L.ntaps;
         mbar_wait_cluster(&B->a_full[ab], aph);
         tc_fence_after();
-        if (lane == 0) dbg_mark(L.dbg, 1, dn);
-        const uint64_t ad_slab = ad_base + (uint64_t)(ab * (Cfg::SLAB / 16));
+        if (lane == 0) dbg_mark(dbg, 1, dn);
+        const uint32_t ad_slab = ad_base + (uint32_t)(ab * (Cfg::SLAB / 16));
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           if (t < ntap) {
-            if (lane == 0) dbg_mark(L.dbg, 3, dn3);
-            mbar_wait_cluster(&B->w_full[ws], wph);
-            tc_fence_after();
-            if (lane == 0) dbg_mark(L.dbg, 3, dn3);
-            const uint64_t ad0 = ad_slab + (uint64_t)(int64_t)(is_res ? 0 : sh[t]);
-            const uint64_t bd0 = bd_base + (uint64_t)(ws * (Cfg2::WSTAGE_MAX / 16));
+            if (!RESW) {
+              mbar_wait_cluster(&B->w_full[ws], wph);
+              tc_fence_after();
+            }
+            const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
+            const uint32_t bd0 = RESW ? bd : bd_base + (uint32_t)ws * w_step;
             const uint32_t first = (uint32_t)(s | t);
             const bool last_tap = t == ntap - 1;
             if (elect_one()) {
               if (fold) {
 #pragma unroll
-                for (int m = 0; m < T; ++m) {
+                for (int m = 0; m < T / 2; ++m) {
 #pragma unroll
                   for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, bd0 + k * w_k16, idesc2, (first | k) != 0);
+                    tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, a_hi, bd0 + k * w_k16, b_hi, idesc2, (first | k) != 0);
 #pragma unroll
                   for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, bd0 + k * w_k16 + w_s16, idesc, 1u);
+                    tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, a_hi, bd0 + k * w_k16 + w_s16, b_hi, idesc, 1u);
                 }
               } else {
 #pragma unroll
-                for (int m = 0; m < T; ++m) {
+                for (int m = 0; m < T / 2; ++m) {
 #pragma unroll
                   for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
 #pragma unroll
                     for (int k = 0; k < TC_KS / 16; ++k)
-                      tc_mma2(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0),
-                              bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), idesc, (first | pass | k) != 0);
+                      tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
+                               bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), b_hi, idesc, (first | pass | k) != 0);
                   }
                 }
               }
-              tc_commit2(&B->w_empty[ws]);
+              if (!RESW) tc_commit2(&B->w_empty[ws]);
               if (last_tap) tc_commit2(&B->a_empty[ab]);
               if (last_tap && s == nslabs - 1) tc_commit2(&B->t_full[tb]);
             }
             __syncwarp();
-            if (++ws == Cfg2::WSTAGES) { ws = 0; wph ^= 1; }
+            if (RESW) bd += w_step;
+            else if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
           }
         }
-        if (++ab == Cfg2::NSLAB) { ab = 0; aph ^= 1; }
+        if (++ab == nsb) { ab = 0; aph ^= 1; }
       }
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);
+      if (lane == 0) dbg_mark(dbg, 1, dn);
       if (++tb == nbuf) { tb = 0; tph ^= 1; }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     if (rank == 0) tc_epilogue<T, false>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, g_first, g_end, g_step);
     else tc_epilogue<T, true>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, g_first, g_end, g_step);
   }
@@ -922,6 +979,7 @@ struct a5_tc_state {
   __half* wpk2_m = nullptr;
   float* bias_m = nullptr;
   int cta2 = 1;                 // use k_tc_conv2 (A5_TC_CTA2=0 selects the single-CTA kernel)
+  int resw = 1;                 // A5_TC_RESW=0: always stream weights through the stage ring
   int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
@@ -975,14 +1033,17 @@ int tc_alloc(a5_net* net) {
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg2<4>::SMEM));
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg2<2>::SMEM));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
   const char* ev;
   tc->t128 = ((ev = getenv("A5_TC_T128")) && atoi(ev) == 2) ? 2 : 4;
   tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
   tc->cta2 = ((ev = getenv("A5_TC_CTA2")) && atoi(ev) == 0) ? 0 : 1;
+  tc->resw = ((ev = getenv("A5_TC_RESW")) && atoi(ev) == 0) ? 0 : 1;
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
@@ -1074,16 +1135,32 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
     if (tc->cta2) {
-      // CTA pairs: T tiles per CTA, 2T per weight stage; TMEM double-buffers for every layer
-      const int T = (D.cout == 32) ? 4 : 2;
+      // CTA pairs: T = 2 tiles per CTA, 4 per weight stage; TMEM double-buffers for every layer
+      constexpr int T = 2;
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
       const int npairs = (ngroups + 1) / 2;
       L.ngroups = ngroups;
       L.wpk = merged ? tc->wpk2_m : tc->wpk2[l];
       const int maxpairs = tc->num_sms / 2;
       const int grid = 2 * (npairs < maxpairs ? npairs : maxpairs);
-      if (T == 4) A5_CUDA(launch_pdl(k_tc_conv2<4>, grid, TC_THREADS, TCfg2<4>::SMEM, st, L, tc->pdl));
-      else A5_CUDA(launch_pdl(k_tc_conv2<2>, grid, TC_THREADS, TCfg2<2>::SMEM, st, L, tc->pdl));
+      const bool h16 = ps.pitch + 1 <= 16;
+      const int slab = h16 ? TCfgH<T, 16>::SLAB : TCfgH<T, 24>::SLAB;
+      const int xr = L.fold ? D.cout : D.cout / 2, sr = D.cout / 2;
+      const int res_slabs = D.res_src >= 0 ? D.res_cin / TC_KS : 0;
+      const int nstage = (D.cin / TC_KS) * 9 + res_slabs;
+      // weights resident in shared memory when the whole set fits beside enough slab buffers: two if
+      // every slab carries nine taps of MMAs, three if one-tap residual slabs must be prefetched past
+      const int wres = (nstage * 4 * (xr + sr) * 16 + 127) & ~127;
+      const int nsb_res = (TC2_SMEM_LIMIT - TC2_MISC - wres) / slab;
+      const bool resw = tc->resw && nsb_res >= (res_slabs ? 3 : 2);
+      L.w_bytes = resw ? wres : TC2_WSTAGES * TC2_WSTAGE_MAX;
+      const int nsb = (TC2_SMEM_LIMIT - TC2_MISC - L.w_bytes) / slab;
+      L.nslab_buf = nsb > 4 ? 4 : nsb;
+      const size_t smem = (size_t)L.nslab_buf * slab + L.w_bytes + TC2_MISC;
+      if (h16 && resw) A5_CUDA(launch_pdl(k_tc_conv2<T, true, 16>, grid, TC2_THREADS, smem, st, L, tc->pdl));
+      else if (h16) A5_CUDA(launch_pdl(k_tc_conv2<T, false, 16>, grid, TC2_THREADS, smem, st, L, tc->pdl));
+      else if (resw) A5_CUDA(launch_pdl(k_tc_conv2<T, true, 24>, grid, TC2_THREADS, smem, st, L, tc->pdl));
+      else A5_CUDA(launch_pdl(k_tc_conv2<T, false, 24>, grid, TC2_THREADS, smem, st, L, tc->pdl));
     } else {
       const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
