@@ -52,10 +52,21 @@ struct EP {
 // --------------------------------------------------------------------------- //
 // per-warp context
 // --------------------------------------------------------------------------- //
+// tooling (a5__debug_step_times): per game, ns spent in the last k_step and what the warp did
+// (bit 0 expanded a leaf, bit 1 played a move, bit 2 finished a game; bits 8.. = selection steps)
+__device__ unsigned long long g_step_dbg[2 * 8192];
+__device__ int g_step_dbg_on = 0;
+__device__ __forceinline__ unsigned long long step_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int NCH>
 struct Warp {
   const EP& P;
   int g, lane;
+  const uint32_t* valid = nullptr;   // shared: anchor masks of the terminal check (warp_valid_masks)
   int8_t* sb;       // shared: board of the position being processed (KB bytes, zero padded)
   float* sf;        // shared: 256 floats of scratch
   uint8_t* nodes;   // this game's node arena
@@ -260,22 +271,52 @@ struct Warp {
     return res;
   }
 
-  // Gamma(alpha < 1): Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha).
-  __device__ float gamma_small(float alpha, int cell) {
+  // Gamma(alpha < 1): Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha).  One attempt, branch-free
+  // (acceptance ~96 %): every draw is addressed by (event counter, cell, attempt) in the Philox stream.
+  __device__ __forceinline__ float gamma_try(float d, float c, float inv_alpha, int cell, uint32_t attempt, bool* ok) const {
+    const uint4 r = rng((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)cell, attempt);
+    const float x = sqrtf(-2.0f * logf(u01(r.x))) * cospif(2.0f * u01(r.y));
+    const float v1 = 1.0f + c * x;
+    const float v = v1 * v1 * v1;
+    const float u = u01(r.z);
+    const float x2 = x * x;
+    // squeeze u < 1 - 0.0331 x^4, else the full log test (NaN for v <= 0 compares false)
+    const bool acc = u < 1.0f - 0.0331f * x2 * x2 || __logf(u) < 0.5f * x2 + d - d * v + d * __logf(v);
+    *ok = v1 > 0.0f && acc;
+    return d * v * exp2f(__log2f(u01(r.w)) * inv_alpha);
+  }
+
+  // Dirichlet numerators for the NCH cells of this lane.  Attempts 0 and 1 of every cell are evaluated
+  // up front as 2*NCH independent instruction streams (a dependent retry loop costs the whole warp a
+  // full latency chain per round, and with 32*NCH draws some lane nearly always rejects once); the
+  // third and later attempts (0.2 % of the cells) run in a rare loop.
+  __device__ __forceinline__ void gamma_cells(float alpha, const bool (&legal)[NCH], float (&gam)[NCH]) const {
     const float d = alpha + 1.0f - 1.0f / 3.0f;
     const float c = rsqrtf(9.0f * d);
-    for (uint32_t attempt = 0; attempt < 24; ++attempt) {
-      uint4 r = rng((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)cell, attempt);
-      float u1 = u01(r.x), u2 = u01(r.y);
-      float x = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-      float v = 1.0f + c * x;
-      if (v <= 0.0f) continue;
-      v = v * v * v;
-      float u = u01(r.z);
-      if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v))
-        return d * v * powf(u01(r.w), 1.0f / alpha);
+    const float inv_alpha = 1.0f / alpha;
+    bool need[NCH];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int cell = k * 32 + lane;
+      bool ok0, ok1;
+      const float g0 = gamma_try(d, c, inv_alpha, cell, 0u, &ok0);
+      const float g1 = gamma_try(d, c, inv_alpha, cell, 1u, &ok1);
+      gam[k] = legal[k] ? (ok0 ? g0 : g1) : 0.0f;
+      need[k] = legal[k] && !ok0 && !ok1;
+      any = any || need[k];
     }
-    return d;
+    if (__any_sync(FULL, any)) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        for (uint32_t attempt = 2; need[k] && attempt < 24; ++attempt) {
+          bool ok;
+          const float gv = gamma_try(d, c, inv_alpha, k * 32 + lane, attempt, &ok);
+          if (ok) { gam[k] = gv; need[k] = false; }
+        }
+        if (need[k]) gam[k] = d;
+      }
+    }
   }
 
   // player.py:230-279.  `nd` is the node of the position in sb.  Returns the chosen cell.
@@ -289,7 +330,8 @@ struct Warp {
     const float* ew = edge_w(nd);
     const float* ep = edge_p(nd);
     int n[NCH];
-    float score[NCH];
+    float wk[NCH], pk[NCH];                      // edge statistics: loaded up front so the HBM latency hides
+    float score[NCH];                            // behind the Dirichlet draw below
     bool legal[NCH];
     float gam[NCH];
     float gsum = 0.0f;
@@ -298,10 +340,16 @@ struct Warp {
       int c = k * 32 + lane;
       legal[k] = c < P.C && sb[c] == 0;
       n[k] = legal[k] ? en[c] : 0;
+      wk[k] = legal[k] ? ew[c] : 0.0f;
+      pk[k] = legal[k] ? ep[c] : 0.0f;
       gam[k] = 0.0f;
-      if (P.training && legal[k]) { gam[k] = gamma_small(P.alpha, c); gsum += gam[k]; }
     }
-    if (P.training) gsum = warp_sum(gsum);
+    if (P.training) {
+      gamma_cells(P.alpha, legal, gam);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) gsum += gam[k];
+      gsum = warp_sum(gsum);
+    }
     const double sq = sqrt((double)(sum_n + 1));
     float best = -INFINITY;
 #pragma unroll
@@ -309,8 +357,8 @@ struct Warp {
       int c = k * 32 + lane;
       score[k] = -INFINITY;
       if (legal[k]) {
-        float p = ep[c];
-        float q = n[k] > 0 ? __fdiv_rn(ew[c], (float)n[k]) : 0.0f;
+        float p = pk[k];
+        float q = n[k] > 0 ? __fdiv_rn(wk[k], (float)n[k]) : 0.0f;
         double t;
         if (P.training) {
           double eta = gsum > 0.0f ? (double)gam[k] / (double)gsum : 0.0;
@@ -559,11 +607,18 @@ struct Warp {
 // --------------------------------------------------------------------------- //
 // kernels
 // --------------------------------------------------------------------------- //
+// Occupancy: the pass is a chain of dependent table reads per game, so resident warps hide it -- 7 CTAs
+// (28 games) per SM put all 4096 games of the benchmark batch on the chip in one wave (measured:
+// 236 us at 3 CTAs/SM, 165 at 4, 125 at 7, spills stay ~100 bytes).
+#ifndef A5_STEP_MINB
+#define A5_STEP_MINB (NCH <= 4 ? 7 : 4)
+#endif
 template <int NCH>
-__global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P, const float* __restrict__ prob,
+__global__ void __launch_bounds__(WPB * 32, A5_STEP_MINB) k_step(const __grid_constant__ EP P, const float* __restrict__ prob,
                                                   const float* __restrict__ value) {
   __shared__ __align__(16) int8_t s_board[WPB][256];
   __shared__ __align__(16) float s_f[WPB][256];
+  __shared__ uint32_t s_valid[WPB][4 * NCH];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * WPB + wid;
   if (g >= P.N) return;
@@ -571,7 +626,11 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
     if (lane == 0) P.need_eval[g] = 0;
     return;
   }
+  const unsigned long long dbg_t0 = g_step_dbg_on ? step_now() : 0ull;
+  unsigned dbg_flags = 0;
   Warp<NCH> W(P, g, lane, s_board[wid], s_f[wid]);
+  warp_valid_masks<NCH>(P.S, P.goal, lane, s_valid[wid]);
+  W.valid = s_valid[wid];
   int8_t* sb = W.sb;
   int sims_left = P.sims_left[g];
   uint32_t own[NCH], opp[NCH];
@@ -587,6 +646,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
     W.backup(P.depth[g], value[g]);
     --sims_left;
     W.st[1] += 1;
+    dbg_flags |= 1u;
   }
 
   int inner = 0;
@@ -611,8 +671,10 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
       __syncwarp();
       warp_step(sb, P.C, action, lane);
       __syncwarp();
-      int code = warp_terminal(sb, P.S, P.goal, lane);
+      W.board_masks(own, opp);
+      int code = warp_terminal_bits<NCH>(own, opp, W.valid, P.S, P.goal, lane);
       W.st[0] += 1;
+      dbg_flags |= code ? 6u : 2u;
       if (code) {                                   // game over: emit, restart (player.py:73)
         W.emit_game(L, code);
         for (int c = lane; c < P.KB; c += 32) sb[c] = 0;
@@ -626,7 +688,6 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
         }
         sims_left = P.sims;
       } else {
-        W.board_masks(own, opp);
         W.collect(own, opp);
         sims_left = W.budget_for_root(own, opp);
         if (lane == 0) { P.root_last[g] = action; P.rec_len[g] = L; }
@@ -647,7 +708,8 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
     int depth = 0;
     uint32_t* path = P.path + (size_t)g * P.C;
     while (true) {
-      int code = warp_terminal(sb, P.S, P.goal, lane);          // before lookup (player.py:214)
+      W.board_masks(own, opp);
+      int code = warp_terminal_bits<NCH>(own, opp, W.valid, P.S, P.goal, lane);   // before lookup (player.py:214)
       if (code) {
         float v = code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f);
         W.backup(depth, v);
@@ -657,7 +719,6 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
         ++inner;
         break;
       }
-      W.board_masks(own, opp);
       uint32_t h = W.hash_masks(own, opp);
       int ep;
       int idx = W.find(h, own, opp, &ep);
@@ -676,6 +737,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
       }
       int cell = W.select(W.node(idx), depth == 0);
       W.st[4] += 1;
+      dbg_flags += 256u;
       if (lane == 0) path[depth] = ((uint32_t)idx << 8) | (uint32_t)cell;
       ++depth;
       __syncwarp();
@@ -688,6 +750,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(const __grid_constant__ EP P,
   if (lane == 0) {
     P.need_eval[g] = pending;
     P.sims_left[g] = sims_left;
+    if (g_step_dbg_on && g < 8192) { g_step_dbg[g] = step_now() - dbg_t0; g_step_dbg[8192 + g] = dbg_flags; }
   }
   W.flush();
 }
@@ -894,7 +957,11 @@ int a5_engine_create(const a5_config* cfg, a5_engine** out) {
   int H = 64;
   while (H < 2 * cap) H <<= 1;
   p.H = H;
-  p.max_inner = cfg->max_inner > 0 ? cfg->max_inner : 16;
+  // lock-step batches: a game that hits terminal positions yields after two NN-free simulations -- the pass
+  // lasts as long as its slowest warp (measured at 4096 games: 2 already collects the +4 % moves per pass
+  // that 16 gives, at a third of the tail); small batches (the B = 1 Player path) keep going to save
+  // host round trips
+  p.max_inner = cfg->max_inner > 0 ? cfg->max_inner : (cfg->n_games >= 256 ? 2 : 16);
   p.node_bytes = 16 + 8 * p.NCH + 12 * p.E;
   p.KB = (int)align_up(p.C, 16);
   p.rec_bb = p.KB;
@@ -1085,4 +1152,11 @@ int a5_engine_counters(a5_engine* e, int64_t* h_out, void* stream) {
   return A5_OK;
 }
 
+// internal tooling (not part of alphafive.h): switch the per-game k_step timing on/off, read it back
+// (h_out: uint64 [2][8192] = ns, flags of the last pass).
+int a5__debug_step_times(int on, unsigned long long* h_out) {
+  A5_CUDA(cudaMemcpyToSymbol(a5::g_step_dbg_on, &on, sizeof(int)));
+  if (h_out) A5_CUDA(cudaMemcpyFromSymbol(h_out, a5::g_step_dbg, sizeof(unsigned long long) * 2 * 8192));
+  return A5_OK;
+}
 }  // extern "C"

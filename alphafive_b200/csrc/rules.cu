@@ -23,11 +23,16 @@ __device__ __forceinline__ void stage_board(const int8_t* g, int8_t* s, int C, i
 
 __global__ void __launch_bounds__(WARPS * 32) k_terminal(const int8_t* boards, int n, int S, int goal, int8_t* codes) {
   __shared__ int8_t sb[WARPS][CMAX];
+  __shared__ uint32_t valid[WARPS][4 * (CMAX / 32)];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int i = blockIdx.x * WARPS + w;
   if (i >= n) return;
+  constexpr int NCH = CMAX / 32;
+  warp_valid_masks<NCH>(S, goal, lane, valid[w]);
   stage_board(boards + (size_t)i * S * S, sb[w], S * S, lane);
-  int code = warp_terminal(sb[w], S, goal, lane);
+  uint32_t own[NCH], opp[NCH];
+  warp_board_masks<NCH>(sb[w], S * S, lane, own, opp);
+  int code = warp_terminal_bits<NCH>(own, opp, valid[w], S, goal, lane);
   if (lane == 0) codes[i] = (int8_t)code;
 }
 

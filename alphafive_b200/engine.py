@@ -4,6 +4,7 @@ Python mirror of the reference's search loop for many games at once: the object 
 the role of N ``genData.player.Player`` instances stepping in lock-step."""
 from __future__ import annotations
 
+import os
 import ctypes as C
 
 import numpy as np
@@ -35,7 +36,7 @@ def make_config(cfg=None, **kw) -> Config:
     c.random_a = int(kw.pop("random_a", False))
     c.auto_play = int(kw.pop("auto_play", False))
     c.node_capacity = kw.pop("node_capacity", 0)
-    c.max_inner = kw.pop("max_inner", 0)
+    c.max_inner = kw.pop("max_inner", int(os.environ.get("A5_MAX_INNER", "0")))
     c.seed = kw.pop("seed", 0)
     c.game_id_base = kw.pop("game_id_base", 0)
     c.record_capacity = kw.pop("record_capacity", 0)

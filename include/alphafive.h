@@ -90,7 +90,8 @@ typedef struct {
                                     0: one get_action per a5_engine_set_roots        */
   int32_t node_capacity;         /* table nodes per game (0 = default)               */
   int32_t max_inner;             /* NN-free (terminal) simulations a game may run in
-                                    one step before yielding (0 = default 16)        */
+                                    one step before yielding (0 = default: 2 for
+                                    batches of >= 256 games, else 16)                */
   uint64_t seed;                 /* Philox key; stream = game_id_base + game index   */
   int64_t game_id_base;          /* global index of local game 0 (rank offset)       */
   int32_t record_capacity;       /* finished-ply records held for harvest (0 = N*S*S) */
