@@ -127,7 +127,11 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
     if (L.head_ch) {
       // head layers (cout = 32): a warp takes whole rows of one M tile, so the 1x1 head conv
       // sees all 32 channels of its position.
-      for (int m = sub; m < T; m += TC_EPI_WARPS / 4) {
+      // the four warps of a lane quadrant share the T tiles; with T = 2 two warps split the 16 policy-head
+      // outputs of a tile between them (each recomputes the 32 activations it needs)
+      constexpr int NPART = (TC_EPI_WARPS / 4) / T > 0 ? (TC_EPI_WARPS / 4) / T : 1;
+      const int part = sub / T;
+      for (int m = sub % T; m < T && (part == 0 || L.head_ch == 16); m += T * NPART) {
         const uint32_t q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
         const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
         const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
             // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8; eight outputs at a time
             __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
 #pragma unroll 1
-            for (int c8 = 0; c8 < 2; ++c8) {
+            for (int c8 = (NPART >= 2 ? part : 0); c8 < (NPART >= 2 ? part + 1 : 2); ++c8) {
               float acc[8];
 #pragma unroll
               for (int c = 0; c < 8; ++c) acc[c] = s_hw[32 * 16 + c8 * 8 + c];
@@ -554,6 +558,20 @@ __device__ __forceinline__ void tc_mma2s(uint32_t d_tmem, uint32_t a_lo, uint32_
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
 }
 
+// Order in which a group's K slabs are consumed: the one-tap residual slabs are spread evenly between the
+// nine-tap main slabs (m0 r0 r1 m1 r2 r3 for 2 + 4), so that every window of (slab buffers - 1)
+// consecutive slabs holds a main slab's worth of MMA time for the prefetch of the slab after it.
+struct SlabSeq {
+  int M, R, mi, ri;
+  __device__ __forceinline__ SlabSeq(int m, int r) : M(m), R(r), mi(0), ri(0) {}
+  // returns true for a residual slab; idx = its index within its kind
+  __device__ __forceinline__ bool next(int& idx) {
+    const bool res = mi == M || ri < (mi * R) / M;
+    idx = res ? ri++ : mi++;
+    return res;
+  }
+};
+
 template <int T, bool RESW, int HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc_conv2(const __grid_constant__ TCLayer L) {
   using Cfg = TCfgH<T, HALO>;
@@ -610,11 +628,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = g_first; g < g_end; g += g_step) {
       const long long r0 = L.row0 + (long long)g * Cfg::ROWS - HALO;
+      SlabSeq seq(main_slabs, res_slabs);
       for (int s = 0; s < nslabs; ++s) {
-        const bool is_res = s >= main_slabs;
+        int sidx;
+        const bool is_res = seq.next(sidx);
         const __half* X = is_res ? L.res : L.src;
         const int xch = is_res ? L.res_ch : L.src_ch;
-        const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
+        const int kc0 = sidx * (TC_KS / 8);
         mbar_wait(&B->a_empty[ab], aph ^ 1);
         if (lane == 0) dbg_mark(L.dbg, 0, dn);
         if (elect_one()) {
@@ -645,16 +665,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     } else {
       int ws = 0, wph = 0;
       for (int g = g_first; g < g_end; g += g_step) {
-        const __half* wsrc = wsrc0;
-        for (int t = 0; t < nstage; ++t) {
-          mbar_wait(&B->w_empty[ws], wph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&B->w_full[ws], stage_bytes);
-            bulk_g2s(w_buf + ws * TC2_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+        SlabSeq seq(main_slabs, res_slabs);
+        for (int s = 0; s < nslabs; ++s) {
+          int sidx;
+          const bool is_res = seq.next(sidx);
+          const int ntap = is_res ? 1 : L.ntaps;
+          // stage (slab, tap) of the packed weights: main stages slab-major, then the residual stages
+          const __half* wsrc = wsrc0 + (size_t)(is_res ? main_slabs * L.ntaps + sidx : sidx * L.ntaps) * stage_bytes;
+          for (int t = 0; t < ntap; ++t) {
+            mbar_wait(&B->w_empty[ws], wph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&B->w_full[ws], stage_bytes);
+              bulk_g2s(w_buf + ws * TC2_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+            }
+            __syncwarp();
+            wsrc += stage_bytes;                           // 2 CTAs x stage_bytes, in halfs
+            if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
           }
-          __syncwarp();
-          wsrc += stage_bytes;                             // 2 CTAs x stage_bytes, in halfs
-          if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
         }
       }
     }
@@ -667,8 +694,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
       __syncwarp();
     }
     for (int g = g_first; g < g_end; g += g_step) {
+      SlabSeq seq(main_slabs, res_slabs);
       for (int s = 0; s < nslabs; ++s) {
-        const int ntap = s >= main_slabs ? 1 : L.ntaps;
+        int sidx;
+        const int ntap = seq.next(sidx) ? 1 : L.ntaps;
         mbar_wait(&B->a_full[ab], aph);
         if (lane == 0) mbar_arrive_remote(&B->a_full[ab], 0);
         __syncwarp();
@@ -711,10 +740,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
       tc_fence_after();
       if (lane == 0) dbg_mark(dbg, 1, dn);
       const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt + m0 * cpt);
-      uint32_t bd = bd_base;                                // RESW: walks through the resident stages
+      SlabSeq seq(main_slabs, res_slabs);
       for (int s = 0; s < nslabs; ++s) {
-        const bool is_res = s >= main_slabs;
+        int sidx;
+        const bool is_res = seq.next(sidx);
         const int ntap = is_res ? 1 : L.ntaps;
+        // RESW: first resident stage of this slab
+        uint32_t bd = bd_base + (uint32_t)(is_res ? main_slabs * L.ntaps + sidx : sidx * L.ntaps) * w_step;
         mbar_wait_cluster(&B->a_full[ab], aph);
         tc_fence_after();
         if (lane == 0) dbg_mark(dbg, 1, dn);
