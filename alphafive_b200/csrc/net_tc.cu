@@ -943,6 +943,232 @@ __global__ void __launch_bounds__(C1_THREADS) k_tc_conv1(const int8_t* __restric
   }
 }
 
+// ------------------------------------------------------------------ conv1 on the tensor cores
+// conv1 (5x5, 3 -> 32, ELU; network.py:63) as a GEMM with an explicit A tile: the inputs are exactly
+// {0, 1} (utils.py:256-272), so A = im2col(planes) is exact in fp16 and only the weights are split:
+//   D[128 positions x 64] = A[128 x 128] * [w_hi | w_lo][128 x 64]     (8 MMAs of K = 16, N = 64)
+// with k = (ky*3 + plane)*8 + kx: one 8-element K chunk (16 bytes) per (kernel row, plane), kx = 5..7 and
+// the 16th chunk zero, so a chunk of the A tile is a 32-entry table lookup on the 5-bit window pattern
+// of that board row.  k_c1_bits turns the int8 planes into bitboards; builder warps extract the 15
+// patterns of their position and write the tile as fp16 {0, 1.0} straight in the tcgen05 K-major
+// layout; one warp issues the MMAs; four warps run the epilogue (hi + lo, bias, ELU, split, store).
+constexpr int C1M_BUILD_WARPS = 4;
+constexpr int C1M_THREADS = 32 * (C1M_BUILD_WARPS + 1 + 4);
+constexpr int C1M_KCH = 16;                                   // K = 128 as 16 chunks of 8 (15 used)
+constexpr int C1M_ATILE = C1M_KCH * 128 * 16;                 // 32 KB
+constexpr int C1M_WBYTES = C1M_KCH * 64 * 16;                 // 16 KB
+constexpr int C1M_BW = 24;                                    // words per board: 8 per input plane
+constexpr int C1M_SMEM = 2 * C1M_ATILE + C1M_WBYTES + 32 * 16 + 128 + 128;
+
+struct __align__(8) C1MBarriers {
+  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+  uint32_t tmem_base, pad;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// int8 planes [n][3][C] -> bitboards [n][plane 3][8 words]: one warp per board.
+__global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ planes, int n, int C, uint32_t* __restrict__ bits) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= n) return;
+  const int8_t* p = planes + (size_t)b * 3 * C;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = k * 32 + lane;
+      const unsigned m = __ballot_sync(FULL, c < C && p[pl * C + c] != 0);
+      if (lane == pl * 8 + k) mine = m;
+    }
+  if (lane < C1M_BW) bits[(size_t)b * C1M_BW + lane] = mine;
+}
+
+__global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __restrict__ bits, const __half* __restrict__ wpk,
+                                                          const float* __restrict__ bias, __half* __restrict__ out,
+                                                          long long plane_rows, int S, int pitch, int per_board, int guard,
+                                                          int n, int ntiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* a_buf = smem;                                       // 2 A tiles [kchunk 10][row 128][8]
+  uint8_t* w_buf = smem + 2 * C1M_ATILE;                       // [kchunk 10][hi 32 | lo 32][8]
+  uint4* s_lut = (uint4*)(w_buf + C1M_WBYTES);                 // window pattern -> 8 halves (5 used)
+  float* s_bias = (float*)(s_lut + 32);
+  C1MBarriers* B = (C1MBarriers*)(s_bias + 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const uint32_t nrows = (uint32_t)n * (uint32_t)per_board;
+
+  for (int i = tid; i < C1M_WBYTES / 16; i += C1M_THREADS) ((uint4*)w_buf)[i] = ((const uint4*)wpk)[i];
+  if (tid < 32) {
+    const uint32_t b = (uint32_t)tid;
+    s_lut[tid] = make_uint4(((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u),
+                            ((b & 4u) ? 0x3C00u : 0u) | ((b & 8u) ? 0x3C000000u : 0u), (b & 16u) ? 0x3C00u : 0u, 0u);
+  }
+  for (int i = tid; i < 2 * 128; i += C1M_THREADS)             // the 16th K chunk of both tiles stays zero
+    *(uint4*)(a_buf + (i >> 7) * C1M_ATILE + (15 * 128 + (i & 127)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) s_bias[tid] = bias[tid];
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B->a_full[i], C1M_BUILD_WARPS); mbar_init(&B->a_empty[i], 1);
+      mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == C1M_BUILD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_proxy_async_smem();                                    // the weights were written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = B->tmem_base;
+
+  if (warp < C1M_BUILD_WARPS) {
+    // ===================== builders: bitboards -> 15 window patterns -> A row =====================
+    // Software-pipelined: the 30 bitboard words of the NEXT tile's position are in flight (one L2 round
+    // trip, row index clamped, result masked later) while the current tile is expanded and stored.
+    const int t = tid;                                         // row of the tile
+    const uint32_t rowbits = (1u << S) - 1u;
+    struct Pos { int rr, cc; bool real; uint32_t lo[5][3], hi[5][3]; };
+    auto fetch = [&](int tile, Pos& P) {
+      const uint32_t q = (uint32_t)tile * 128u + (uint32_t)t;
+      const uint32_t board = q / (uint32_t)per_board, within = q - board * (uint32_t)per_board;
+      P.rr = (int)(within / (uint32_t)pitch);
+      P.cc = (int)within - P.rr * pitch;
+      P.real = tile < ntiles && q < nrows && P.rr < S && P.cc < S;
+      const uint32_t* bw = bits + (size_t)(P.real ? board : 0u) * C1M_BW;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        const int r = min(max(P.rr + ky - 2, 0), S - 1);
+        const int wd = (r * S) >> 5;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          P.lo[ky][p] = __ldg(bw + p * 8 + wd);
+          P.hi[ky][p] = __ldg(bw + p * 8 + min(wd + 1, 7));
+        }
+      }
+    };
+    int ab = 0, aph = 0;
+    Pos cur, nxt;
+    fetch(blockIdx.x, cur);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      fetch(tile + gridDim.x, nxt);
+      uint32_t pat[3][5];
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        const int r = cur.rr + ky - 2;
+        const bool ok = cur.real && r >= 0 && r < S;
+        const int sh = (min(max(r, 0), S - 1) * S) & 31;        // row r = bits [r S, r S + S) of the 8-word bitboard
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t row = __funnelshift_r(cur.lo[ky][p], cur.hi[ky][p], sh) & rowbits;
+          pat[p][ky] = ok ? ((row << 2) >> cur.cc) & 31u : 0u;  // columns cc-2 .. cc+2
+        }
+      }
+      mbar_wait(&B->a_empty[ab], aph ^ 1);
+      uint8_t* arow = a_buf + ab * C1M_ATILE + t * 16;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) *(uint4*)(arow + (ky * 3 + p) * 128 * 16) = s_lut[pat[p][ky]];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->a_full[ab]);
+      if (++ab == 2) { ab = 0; aph ^= 1; }
+      cur = nxt;
+    }
+  } else if (warp == C1M_BUILD_WARPS) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = instr_desc(128, 64);
+    const uint64_t ad_base = smem_desc(smem_u32(a_buf), 128 * 16, 128);
+    const uint64_t bd_base = smem_desc(smem_u32(w_buf), 64 * 16, 128);
+    int ab = 0, aph = 0, tb = 0, tph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&B->t_empty[tb], tph ^ 1);
+      mbar_wait(&B->a_full[ab], aph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < C1M_KCH / 2; ++k)
+          tc_mma(tmem + (uint32_t)(tb * 64), ad_base + (uint64_t)(ab * (C1M_ATILE / 16) + k * (2 * 128 * 16 / 16)),
+                 bd_base + (uint64_t)(k * (2 * 64 * 16 / 16)), idesc, k != 0);
+        tc_commit(&B->a_empty[ab]);
+        tc_commit(&B->t_full[tb]);
+      }
+      __syncwarp();
+      if (++ab == 2) { ab = 0; aph ^= 1; }
+      if (++tb == 2) { tb = 0; tph ^= 1; }
+    }
+  } else {
+    // ===================== epilogue: hi + lo, bias, ELU, hi/lo split, store =====================
+    const int quad = warp & 3;
+    int tb = 0, tph = 0;
+    constexpr float K_ACC = 1.0f / W_SCALE;
+    constexpr float K_L2E = 1.4426950408889634f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t q = (uint32_t)tile * 128u + (uint32_t)(quad * 32 + lane);
+      const uint32_t within = q % (uint32_t)per_board;
+      const int rr = (int)(within / (uint32_t)pitch), cc = (int)within - rr * pitch;
+      const bool real = q < nrows && rr < S && cc < S;
+      const long long row = guard + (long long)q;
+      mbar_wait(&B->t_full[tb], tph);
+      tc_fence_after();
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t v[16], v2[16];
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * 64 + h2 * 16);
+        tc_ld16(taddr, v);
+        tc_ld16(taddr + 32u, v2);
+        tc_ld_wait();
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = kc * 8 + e * 2 + h;
+              const float a = fmaf(__uint_as_float(v[c]) + __uint_as_float(v2[c]), K_ACC, s_bias[h2 * 16 + c]);
+              x[h] = (a > 0.0f ? a : ex2_approx(a * K_L2E) - 1.0f) * ACT_SCALE;
+            }
+            const __half2 hh = __floats2half2_rn(x[0], x[1]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(x[0] - hf.x, x[1] - hf.y);
+            hi[e] = real ? *(const uint32_t*)&hh : 0u;
+            lo[e] = real ? *(const uint32_t*)&ll : 0u;
+          }
+          const long long chunk = h2 * 2 + kc;
+          *(uint4*)(out + (chunk * plane_rows + row) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *(uint4*)(out + ((4 + chunk) * plane_rows + row) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->t_empty[tb]);
+      if (++tb == 2) { tb = 0; tph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C1M_BUILD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  }
+}
+
+// conv1 weights [75][ldw] f32 (row (ky*5 + kx)*3 + plane) -> [kchunk 16 = ky*3 + plane][w_hi ch 0..31 | w_lo ch 0..31][kx 8]
+// fp16, scaled by 2^10; kx >= 5 and chunk 15 are zero
+__global__ void k_c1m_pack(const float* __restrict__ w, int ldw, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C1M_KCH * 64 * 8) return;
+  const int j = i / (64 * 8), r = (i / 8) % 64, e = i % 8;
+  const int ky = j / 3, p = j - ky * 3, ch = r & 31;
+  const float x = (j < 15 && e < 5) ? w[(size_t)((ky * 5 + e) * 3 + p) * ldw + ch] * W_SCALE : 0.0f;
+  const __half h = __float2half_rn(x);
+  out[i] = (r >> 5) ? __float2half_rn(x - __half2float(h)) : h;
+}
+
 // TF kernel [taps][cin][cout] (+ optional res [1][rcin][cout]) -> per-(slab, tap) stages
 // [kchunk 4][hi|lo][cout][8] fp16, scaled by 2^10 (hi and lo adjacent along N, so one
 // N = 2*cout descriptor covers both).
@@ -1010,6 +1236,9 @@ struct a5_tc_state {
   // ~44-cycle MMA floor, and the 128-channel input is read once)
   __half* wpk2_m = nullptr;
   float* bias_m = nullptr;
+  __half* wpk_c1 = nullptr;     // conv1 weights for k_tc_conv1m
+  uint32_t* c1_bits = nullptr;  // bitboards of the input planes (k_c1_bits)
+  int conv1_tc = 1;             // A5_TC_CONV1=table: the CUDA-core table-lookup conv1
   int cta2 = 1;                 // use k_tc_conv2 (A5_TC_CTA2=0 selects the single-CTA kernel)
   int resw = 1;                 // A5_TC_RESW=0: always stream weights through the stage ring
   int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
@@ -1062,6 +1291,9 @@ int tc_alloc(a5_net* net) {
   }
   A5_CUDA(cudaMalloc(&tc->wpk2_m, (size_t)(128 / TC_KS) * 9 * 2 * 4 * 96 * 8 * sizeof(__half)));
   A5_CUDA(cudaMalloc(&tc->bias_m, 96 * sizeof(float)));
+  A5_CUDA(cudaMalloc(&tc->wpk_c1, C1M_WBYTES));
+  A5_CUDA(cudaMalloc(&tc->c1_bits, (size_t)net->max_batch * C1M_BW * sizeof(uint32_t)));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_conv1m, cudaFuncAttributeMaxDynamicSharedMemorySize, C1M_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
@@ -1077,6 +1309,7 @@ int tc_alloc(a5_net* net) {
   tc->cta2 = ((ev = getenv("A5_TC_CTA2")) && atoi(ev) == 0) ? 0 : 1;
   tc->resw = ((ev = getenv("A5_TC_RESW")) && atoi(ev) == 0) ? 0 : 1;
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
+  tc->conv1_tc = ((ev = getenv("A5_TC_CONV1")) && !strcmp(ev, "table")) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
@@ -1093,6 +1326,8 @@ void tc_free(a5_net* net) {
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk2[i]);
   cudaFree(net->tc->wpk2_m);
   cudaFree(net->tc->bias_m);
+  cudaFree(net->tc->wpk_c1);
+  cudaFree(net->tc->c1_bits);
   heads_free(net->tc->heads);
   delete net->tc;
   net->tc = nullptr;
@@ -1110,6 +1345,8 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     k_tc_pack2<<<256, 256, 0, st>>>(w, nullptr, 0, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
     A5_CUDA(cudaGetLastError());
   }
+  k_c1m_pack<<<(C1M_KCH * 64 * 8 + 255) / 256, 256, 0, st>>>(net->w[0], 64, tc->wpk_c1);
+  A5_CUDA(cudaGetLastError());
   k_tc_pack2<<<256, 256, 0, st>>>(t[T_B3_C1_K], t[T_B4_C1_K], 32, nullptr, 9, 128, 0, 96, 0, tc->wpk2_m);
   A5_CUDA(cudaGetLastError());
   A5_CUDA(cudaMemcpyAsync(tc->bias_m, net->bias[5], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1128,10 +1365,20 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   a5_tc_state* tc = net->tc;
   PosSpace ps(net->S);
   TC_MARK(0);
-  const int nb1 = (n + C1_NB - 1) / C1_NB;
-  const int grid1 = nb1 < 3 * tc->num_sms ? nb1 : 3 * tc->num_sms;
-  k_tc_conv1<<<grid1, C1_THREADS, C1_SMEM, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
-                                   ps.per_board, ps.guard, n);
+  const long long nrows1 = (long long)n * ps.per_board;
+  if (tc->conv1_tc) {
+    const int ntiles = (int)((nrows1 + 127) / 128);
+    const int grid1 = ntiles < 2 * tc->num_sms ? ntiles : 2 * tc->num_sms;
+    k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits);
+    A5_CUDA(cudaGetLastError());
+    k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
+                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles);
+  } else {
+    const int nb1 = (n + C1_NB - 1) / C1_NB;
+    const int grid1 = nb1 < 3 * tc->num_sms ? nb1 : 3 * tc->num_sms;
+    k_tc_conv1<<<grid1, C1_THREADS, C1_SMEM, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
+                                     ps.per_board, ps.guard, n);
+  }
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
