@@ -335,9 +335,10 @@ def run_ours(a):
 
 
 def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
-    """Dominant kernel = k_tc_conv (ten launches per pass, 98.9 % of the algorithmic FLOPs).
-    achieved = algorithmic conv FLOPs of one pass / summed CUDA-event time of its ten launches."""
-    whole = {"kernel": "whole net forward (12 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
+    """Dominant kernel = k_tc_conv2 (nine launches per pass -- block3-conv1 and block4-conv1 run as one
+    layer -- 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass / summed
+    CUDA-event time of those launches."""
+    whole = {"kernel": "whole net forward (bitboards + conv1 + 9 block convs + heads = 12 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
              "ms_per_pass": nn_ms, "flop_per_leaf": flop}
     if lt is None:
         return {"bound": "tensor", "kernel": "policy/value net forward, fp32 CUDA-core path", "achieved": nn_tflops,
@@ -347,7 +348,7 @@ def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
     conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
     ach = conv_flop / (conv_ms / 1000) / 1e12
     tr = measured_traffic()
-    return {"bound": "tensor", "kernel": "k_tc_conv (tcgen05 3x3 conv + residual, 10 launches per pass)",
+    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 9 launches per pass)",
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
             "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
             "traffic": tr.get("conv_dram_bytes_per_pass") if tr else None,
@@ -358,7 +359,7 @@ def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
 
 
 def launches_per_pass(mode):
-    # tensor-core path: conv1 + 10 block convs + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
+    # tensor-core path: bitboards + conv1 + 9 block convs + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
     return 12 if mode == 1 else 15
 
 
