@@ -147,14 +147,14 @@ def run_reference(a):
     wall = time.perf_counter() - t0
     v = tot_m / a.steps
     sample = f"{workers} processes x 1 move of {sims} sims per step from the empty board, training mode, oracle port + torch-CPU fp32 net (1 thread each)"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "moves/s", "leaf_evals_per_s": tot_e / a.steps,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * wall / max(1, a.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, 1), "board": S, "sims": sims, "upper_sims": upper},
+        "config": {"workload": workload_name(a, max(1, a.gpus)), "board": S, "sims": sims, "upper_sims": upper},
         "cpu_baseline": {"value": v, "unit": "moves/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
 
 
 def workload_name(a, world):
@@ -329,7 +329,7 @@ def run_ours(a):
                                    "leaf_evals_per_s": ev, "five_workers": {"value": v5, "leaf_evals_per_s": ev5},
                                    "sample": f"{cores} processes x 2 moves of {sims} sims from the empty board, oracle port "
                                              f"(numpy MCTS + torch-CPU fp32 net, 1 thread each), {wall:.1f}s wall"}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -388,8 +388,20 @@ def measured_traffic():
         return None
 
 
+def emit(line: str):
+    """The one JSON line goes to the process's real stdout (see main)."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     args = parse()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL writes its version banner to
+    # stdout under NCCL_DEBUG=VERSION) are sent to stderr for the whole run
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
