@@ -397,16 +397,25 @@ struct Warp {
   // already staged in sb.
   __device__ void expand(const float* prob_row, uint32_t h, int slot_pos,
                          const uint32_t (&own)[NCH], const uint32_t (&opp)[NCH]) {
-    for (int c = lane; c < P.C; c += 32) sf[c] = prob_row[c];
+    // priors of the legal cells, +0.0f elsewhere (x + 0.0f == x exactly, so the masked sequential sum below
+    // equals the reference's sum over the legal cells only); KB is a multiple of 16, the pad stays zero
+    int nlegal = 0;
+    for (int c = lane; c < P.KB; c += 32) {
+      const bool lg = c < P.C && sb[c] == 0;
+      sf[c] = lg ? prob_row[c] : 0.0f;
+      nlegal += lg;
+    }
+    nlegal = warp_sum_i(nlegal);
     __syncwarp();
     float tot = 0.0f;
-    int nlegal = 0;
     if (lane == 0) {
-      for (int c = 0; c < P.C; ++c)
-        if (sb[c] == 0) { tot = __fadd_rn(tot, sf[c]); ++nlegal; }   // sequential f32 sum, row-major
+      const float4* s4 = (const float4*)sf;
+      for (int c4 = 0; c4 < P.KB / 4; ++c4) {                   // sequential f32 sum, row-major (player.py:198)
+        const float4 v = s4[c4];
+        tot = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(tot, v.x), v.y), v.z), v.w);
+      }
     }
     tot = __shfl_sync(FULL, tot, 0);
-    nlegal = __shfl_sync(FULL, nlegal, 0);
     const float denom = 1e-5f > tot ? 1e-5f : tot;
     st[2] += 1;
     st[5] += nlegal;

@@ -162,10 +162,18 @@ class SearchEngine:
                     prob.copy_(torch.from_numpy(p))
                     value.copy_(torch.from_numpy(v))
             else:
-                net.forward_raw(self.planes_ptr, self.N, prob, value)
-                it += 1
-                if it % check_every == 0 and self.busy() == 0:
+                # every pass completes at least one simulation per busy game, so the largest remaining
+                # budget bounds the passes still needed: run them back to back (no host sync in between),
+                # then look again (games that met terminal positions finished early; `check_every` only
+                # bounds the first burst when the budgets are not known to be small)
+                left = max(1, int(self.sims_left().max().item()))
+                for _ in range(left):
+                    net.forward_raw(self.planes_ptr, self.N, prob, value)
+                    self.step(prob, value)
+                it += left
+                if self.busy() == 0:
                     break
+                continue
             self.step(prob, value)
         return it
 
