@@ -15,6 +15,7 @@ import torch
 
 from . import rules as _rules
 from .genData.player import board_to_state, construct_weights, state_to_board  # noqa: F401  (re-exported)
+from .replay_stack import RandomStack  # noqa: F401  (utils.py:14-146, device-resident)
 
 BLACK_WIN = 1          # utils.py:9-11
 WHITE_WIN = -1

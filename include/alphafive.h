@@ -179,6 +179,16 @@ int a5_engine_harvest(a5_engine* e, void* d_out, int max_records, int32_t* h_cou
 int a5_engine_counters(a5_engine* e, int64_t* h_out, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Replay buffer sampling.  Replaces the gather / augmentation loop of
+ * RandomStack.get_data (utils.py:118-146): d_records is a device array of ply records
+ * (a5_record_stride(S) bytes each); sample i is record d_idx[i] under np.rot90(k = d_rot[i])
+ * followed by np.flip(axis 0) when d_flip[i] != 0, the last move remapped alike
+ * (utils.py:129-140), expanded by board_to_inputs (utils.py:256-272).
+ * d_boards f32[num][3][S][S], d_weights f32[num], d_values f32[num], d_policies f32[num][S*S]. */
+int a5_replay_sample(const void* d_records, int S, const int64_t* d_idx, const uint8_t* d_rot, const uint8_t* d_flip,
+                     int num, float* d_boards, float* d_weights, float* d_values, float* d_policies, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Policy/value network forward.  Replaces ResNet.eval (network.py:90-97), i.e. the
  * pv_fn seam (player.py:190-192) and the batch eval inside NetworkAPI
  * (networkAPI.py:67-68).

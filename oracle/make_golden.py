@@ -17,6 +17,8 @@ mcts_train_11.npz    seeded training-mode summary statistics (distributional pin
 replay_sample.npz    1,024 records + 3 whole games of data_buffer/data6960.pkl
 ckpt6960.npz         the 42 tensors of ckpt/alphaFive-6960 (via alphafive_b200.ckpt)
 weights.npz          construct_weights(L, 0.94) for L = 1..64
+replay_stack.npz     utils.RandomStack driven with seeded generators: accept flags and
+                     bookkeeping after every push, one get_data batch
 """
 from __future__ import annotations
 
@@ -290,14 +292,60 @@ def make_weights(utils):
     np.savez_compressed(os.path.join(OUT, "weights.npz"), w=ws)
 
 
+def make_replay_stack(utils):
+    """Drive the real RandomStack (utils.py:14-146) with games cut from the shipped replay buffer."""
+    import io
+    import contextlib
+    data = pickle.load(open(f"{REF}/data_buffer/data6960.pkl", "rb"))
+    lens = pickle.load(open(f"{REF}/data_buffer/data_len6960.pkl", "rb"))
+    res = pickle.load(open(f"{REF}/data_buffer/result6960.pkl", "rb"))
+    total = int(np.sum(lens))
+    offs = np.concatenate([[0], np.cumsum(lens)]) + (len(data) - total)
+    S = 11
+    rng = np.random.default_rng(21)
+    games = [int(g) for g in rng.choice(np.arange(1, len(lens)), 120, replace=False)]
+    random.seed(1234)
+    np.random.seed(4321)
+    stack = utils.RandomStack(S, length=900)                # small: eviction happens many times
+    accepted, n_data, black, white, first_len, n_games = [], [], [], [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):         # push prints statistics
+        for g in games:
+            game = data[int(offs[g]):int(offs[g + 1])]
+            accepted.append(stack.push(list(game), int(res[g])))
+            n_data.append(len(stack.data)); black.append(stack.black_win); white.append(stack.white_win)
+            first_len.append(stack.data_len[0] if stack.data_len else 0); n_games.append(len(stack.data_len))
+    boards, weights, values, policies = stack.get_data(256)
+    la = np.array([r[2] if r[2] is not None else (-1, -1) for r in stack.data], np.int16)
+    np.savez_compressed(
+        os.path.join(OUT, "replay_stack.npz"), games=np.array(games), length=900,
+        g_off=np.array([[int(offs[g]), int(offs[g + 1])] for g in games]), g_result=np.array([res[g] for g in games]),
+        g_states=np.array([r[0] for g in games for r in data[int(offs[g]):int(offs[g + 1])]]),
+        g_policy=np.stack([r[1] for g in games for r in data[int(offs[g]):int(offs[g + 1])]]).astype(np.float32),
+        g_last=np.array([r[2] if r[2] is not None else (-1, -1) for g in games
+                         for r in data[int(offs[g]):int(offs[g + 1])]], np.int16),
+        g_value=np.array([r[3] for g in games for r in data[int(offs[g]):int(offs[g + 1])]], np.float32),
+        g_weight=np.array([r[4] for g in games for r in data[int(offs[g]):int(offs[g + 1])]], np.float32),
+        accepted=np.array(accepted), n_data=np.array(n_data), black=np.array(black), white=np.array(white),
+        first_len=np.array(first_len), n_games=np.array(n_games),
+        final_states=np.array([r[0] for r in stack.data]), final_last=la,
+        final_data_len=np.array(stack.data_len), final_result=np.array(stack.result),
+        batch_boards=boards, batch_weights=weights, batch_values=values, batch_policies=policies,
+        seeds=np.array([1234, 4321]))
+    print("replay_stack:", sum(accepted), "of", len(games), "games accepted,", len(stack.data), "records held")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--replay-stack-only" in sys.argv:
+        make_replay_stack(_ref()[0])
+        return
     utils, config, Player = _ref()
     if "--mcts-only" not in sys.argv:
         make_rules(11, utils, 3000, 11)
         make_rules(15, utils, 1500, 15)
         make_weights(utils)
         make_replay(utils)
+        make_replay_stack(utils)
         make_ckpt()
     rs = np.load(os.path.join(OUT, "replay_sample.npz"))
     roots11 = [(np.zeros((11, 11), np.int8), None)]
