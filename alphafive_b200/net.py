@@ -51,9 +51,10 @@ def glorot_init(S: int, seed: int = 0) -> dict[str, np.ndarray]:
 
 
 class DeviceNet:
-    """eval(planes) -> (prob, value) on the device; ``mode`` selects the compute path."""
+    """eval(planes) -> (prob, value) on the device.  ``mode``: ``NET_TC`` (default) is the tcgen05 path;
+    ``NET_FP32`` is the exact-fp32 CUDA-core path kept as the on-device reference for debugging."""
 
-    def __init__(self, S: int, max_batch: int, weights: dict | None = None, mode: int = NET_FP32, device=None):
+    def __init__(self, S: int, max_batch: int, weights: dict | None = None, mode: int = NET_TC, device=None):
         self.lib = _lib.load()
         self.S, self.C, self.max_batch, self.mode = S, S * S, max_batch, mode
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
