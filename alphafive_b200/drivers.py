@@ -77,6 +77,57 @@ def gen_data_lockstep(selfplay, passes_per_poll=None):
 
 
 # ------------------------------------------------------------------------------------
+# main.py:29-78 -- the training loop, everything on the device
+# ------------------------------------------------------------------------------------
+def train_loop(config, n_games=4096, total_step=None, restore=None, seed=0, save_every=60, save_dir=None,
+               passes_per_poll=None, log=print):
+    """``main.main`` without the worker processes: lock-step self-play feeds the device-resident
+    ``RandomStack``; every accepted game, once the buffer is full, is followed by four minibatches of
+    ``config.batch_size`` (main.py:61-68) with the learning rate of ``config.get_lr(step)``; the new weights
+    go back into the search net after every harvest (the reference's workers see every update through
+    the shared session).  Returns (trainer, stack, step)."""
+    import numpy as np
+    from .genData.network import ResNet
+    from .replay import HEADER_BYTES
+    from .selfplay import SelfPlay
+    from .train import Trainer
+    from .utils import RandomStack
+    S = config.board_size
+    total_step = config.total_step if total_step is None else total_step
+    stack = RandomStack(board_size=S, length=config.buffer_size)
+    net = ResNet(S, max_batch=n_games, seed=seed)
+    if restore:
+        net.restore(restore)
+    trainer = Trainer(S, {k: v.cpu().numpy() for k, v in net.device_net.params.items()})
+    sp = SelfPlay(config, n_games=n_games, net=net.device_net, training=True, seed=seed)
+    sp.start()
+    step = 1
+    while step < total_step:
+        sp.run_passes(passes_per_poll or config.simulation_per_step)
+        records, _ = sp.harvest()
+        if records.shape[0] == 0:
+            continue
+        head = records[:, :HEADER_BYTES].cpu().numpy()
+        lens = head[:, 14:16].copy().view(np.int16).reshape(-1)
+        res = head[:, 28:32].copy().view(np.int32).reshape(-1)
+        i = 0
+        while i < records.shape[0] and step < total_step:
+            n = int(lens[i])
+            accepted = stack.push(records[i:i + n], int(res[i]))      # main.py:61
+            i += n
+            if accepted and stack.is_full():                           # main.py:62
+                for _ in range(4):
+                    out = trainer.step(*stack.get_data_device(config.batch_size), lr=config.get_lr(step))
+                step += 1
+                log("step: %d, xcross_loss: %0.3f, mse: %0.3f, entropy: %0.3f" % (step, *out))
+                if save_dir and step % save_every == 0:
+                    np.savez(f"{save_dir}/alphaFive-{step}.npz", **{k.replace("/", "__"): v for k, v in trainer.weights().items()})
+                    stack.save(step, directory=save_dir)
+        trainer.sync_to(net)
+    return trainer, stack, step
+
+
+# ------------------------------------------------------------------------------------
 # choose_best_player.py:42-72 -- arena between two weight sets
 # ------------------------------------------------------------------------------------
 def count_wins(winners, early_stop_after=30):

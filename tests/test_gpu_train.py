@@ -1,0 +1,93 @@
+"""Device training step (alphafive_b200.train.Trainer: torch autograd fp32 + TF-Adam) against the
+float64 oracle, and the closed loop self-play -> RandomStack -> Trainer -> DeviceNet."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(n=256):
+    z = golden("replay_stack.npz")
+    return z["batch_boards"][:n], z["batch_weights"][:n], z["batch_values"][:n], z["batch_policies"][:n]
+
+
+@pytest.mark.parametrize("init", ["glorot", "ckpt"])
+def test_three_steps_match_float64_oracle(cuda_lib, init):
+    from alphafive_b200.train import Trainer
+    from oracle.train import OracleTrainer
+    if init == "ckpt":
+        z = golden("ckpt6960.npz")
+        w0 = {k.replace("__", "/"): z[k] for k in z.files}
+    else:
+        w0 = onet.glorot_weights(11, 0)
+    b, w, v, p = _batch(128)
+    dev, ora = Trainer(11, w0), OracleTrainer(11, w0)
+    for step in range(3):
+        got, want = dev.step(b, w, v, p, lr=1e-3), ora.step(b, w, v, p, lr=1e-3)
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-5), (step, got, want)
+    gw, ww = dev.weights(), ora.weights()
+    for k in ww:
+        d = np.abs(gw[k].astype(np.float64) - ww[k])
+        # fp32 vs fp64 gradients: entries whose gradient is ~0 may step the other way (|step| <= lr)
+        assert d.mean() < 2e-6 and (d > 2e-5).mean() < 2e-3 and d.max() <= 3 * 1e-3 + 1e-6, (k, d.mean(), d.max())
+
+
+def test_closed_loop_selfplay_replay_train_reload(cuda_lib):
+    import torch
+    from alphafive_b200.net import DeviceNet, glorot_init
+    from alphafive_b200.selfplay import SelfPlay
+    from alphafive_b200.train import Trainer
+    from alphafive_b200.utils import RandomStack
+    S, N = 11, 128
+    w0 = glorot_init(S, 0)
+    net = DeviceNet(S, N, w0)
+    sp = SelfPlay(None, n_games=N, net=net, training=True, seed=1, board_size=S, simulation_per_step=10,
+                  upper_simulation_per_step=14)
+    sp.start()
+    random.seed(0)
+    np.random.seed(0)
+    stack = RandomStack(S, length=600)
+    for _ in range(60):
+        sp.run_passes(40)
+        stack.push_records(sp.harvest()[0])
+        if stack.is_full():
+            break
+    assert stack.is_full()
+    tr = Trainer(S, w0)
+    first = None
+    for _ in range(8):
+        b, w, v, p = stack.get_data_device(256)
+        x = tr.step(b, w, v, p, lr=1e-3)
+        first = first or x
+    assert x[0] < first[0]                                   # policy cross-entropy went down
+    x0 = np.zeros((4, 3, S, S), np.float32)
+    p_before, _ = net.eval(x0)
+    tr.sync_to(net)
+    p_after, _ = net.eval(x0)
+    want_p, _ = onet.OracleNet(S, tr.weights()).eval(x0)
+    assert np.abs(p_after - want_p).max() < 1e-4 and np.abs(p_after - p_before).max() > 1e-5
+    sp.run_passes(20)                                        # the search keeps running on the new weights
+    torch.cuda.synchronize()
+
+
+def test_train_loop_driver(cuda_lib, tmp_path):
+    """main.py:29-78 restated (drivers.train_loop): a few optimiser steps end to end on the device."""
+    import types
+    from alphafive_b200 import config as base
+    from alphafive_b200.drivers import train_loop
+    cfg = types.SimpleNamespace(**{k: v for k, v in vars(base).items() if not k.startswith("_")})
+    cfg.simulation_per_step, cfg.upper_simulation_per_step = 10, 14
+    cfg.buffer_size, cfg.batch_size, cfg.total_step = 400, 64, 4
+    random.seed(2)
+    np.random.seed(2)
+    lines = []
+    trainer, stack, step = train_loop(cfg, n_games=128, seed=3, save_every=2, save_dir=str(tmp_path),
+                                      passes_per_poll=60, log=lines.append)
+    assert step == 4 and trainer.t == 12 and stack.is_full() and len(lines) == 3
+    assert lines[0].startswith("step: 2, xcross_loss: ")
+    assert (tmp_path / "alphaFive-2.npz").exists() and (tmp_path / "data2.pkl").exists()
