@@ -273,9 +273,10 @@ struct Warp {
 
   // Gamma(alpha < 1): Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha).  One attempt, branch-free
   // (acceptance ~96 %): every draw is addressed by (event counter, cell, attempt) in the Philox stream.
+  // Fast-math intrinsics: the variates only feed exploration noise (parity there is distributional).
   __device__ __forceinline__ float gamma_try(float d, float c, float inv_alpha, int cell, uint32_t attempt, bool* ok) const {
     const uint4 r = rng((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)cell, attempt);
-    const float x = sqrtf(-2.0f * logf(u01(r.x))) * cospif(2.0f * u01(r.y));
+    const float x = __fsqrt_rn(-2.0f * __logf(u01(r.x))) * __cosf(6.283185307179586f * u01(r.y));
     const float v1 = 1.0f + c * x;
     const float v = v1 * v1 * v1;
     const float u = u01(r.z);
@@ -286,35 +287,48 @@ struct Warp {
     return d * v * exp2f(__log2f(u01(r.w)) * inv_alpha);
   }
 
-  // Dirichlet numerators for the NCH cells of this lane.  Attempts 0 and 1 of every cell are evaluated
-  // up front as 2*NCH independent instruction streams (a dependent retry loop costs the whole warp a
-  // full latency chain per round, and with 32*NCH draws some lane nearly always rejects once); the
-  // third and later attempts (0.2 % of the cells) run in a rare loop.
+  // Dirichlet numerators for the NCH cells of this lane.  Attempt 0 of every cell runs as NCH independent
+  // instruction streams; the ~4 % rejected (lane, cell) pairs of the warp are then compacted -- the j-th
+  // reject is retried by lane j -- so the retries cost one more stream instead of NCH (a per-lane retry
+  // loop costs the whole warp a latency chain per round, and some lane nearly always rejects).
   __device__ __forceinline__ void gamma_cells(float alpha, const bool (&legal)[NCH], float (&gam)[NCH]) const {
     const float d = alpha + 1.0f - 1.0f / 3.0f;
     const float c = rsqrtf(9.0f * d);
     const float inv_alpha = 1.0f / alpha;
-    bool need[NCH];
-    bool any = false;
+    unsigned rej[NCH];
+    int total = 0;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      const int cell = k * 32 + lane;
-      bool ok0, ok1;
-      const float g0 = gamma_try(d, c, inv_alpha, cell, 0u, &ok0);
-      const float g1 = gamma_try(d, c, inv_alpha, cell, 1u, &ok1);
-      gam[k] = legal[k] ? (ok0 ? g0 : g1) : 0.0f;
-      need[k] = legal[k] && !ok0 && !ok1;
-      any = any || need[k];
+      bool ok0;
+      const float g0 = gamma_try(d, c, inv_alpha, k * 32 + lane, 0u, &ok0);
+      gam[k] = legal[k] ? g0 : 0.0f;
+      rej[k] = __ballot_sync(FULL, legal[k] && !ok0);
+      total += __popc(rej[k]);
     }
-    if (__any_sync(FULL, any)) {
+    for (int base = 0; base < total; base += 32) {           // rounds of 32 rejects (one round in practice)
+      const int j = base + lane;                             // the reject this lane retries
+      int cell = -1, cum = 0;
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
-        for (uint32_t attempt = 2; need[k] && attempt < 24; ++attempt) {
-          bool ok;
-          const float gv = gamma_try(d, c, inv_alpha, k * 32 + lane, attempt, &ok);
-          if (ok) { gam[k] = gv; need[k] = false; }
+        const int n = __popc(rej[k]);
+        if (cell < 0 && j < cum + n) cell = k * 32 + (int)__fns(rej[k], 0, j - cum + 1);
+        cum += n;
+      }
+      float val = d;
+      if (cell >= 0) {
+        bool ok = false;
+        for (uint32_t attempt = 1; !ok && attempt < 24; ++attempt) {
+          const float gv = gamma_try(d, c, inv_alpha, cell, attempt, &ok);
+          if (ok) val = gv;
         }
-        if (need[k]) gam[k] = d;
+      }
+      cum = 0;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int src = cum + __popc(rej[k] & ((1u << lane) - 1u)) - base;   // who retried (lane, k)
+        const float got = __shfl_sync(FULL, val, src & 31);
+        if (((rej[k] >> lane) & 1u) && src >= 0 && src < 32) gam[k] = got;
+        cum += __popc(rej[k]);
       }
     }
   }
