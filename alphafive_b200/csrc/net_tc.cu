@@ -18,9 +18,9 @@
 // The 1x1 projection of a residual block is one more K segment of conv2 reading the block
 // input, so skip-add + bias + ELU + hi/lo re-split are all in the epilogue.
 //
-// One persistent CTA per SM; per CTA a group of 4 M-tiles (512 positions) shares every weight
-// stage (4*Cout <= 512 TMEM columns).  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer,
-// 2..5 = epilogue (TMEM -> registers -> bias/ELU/split -> coalesced 16-byte stores).
+// One persistent CTA per SM, clusters of two (tcgen05 cta_group::2): see k_tc_conv2 below for the warp
+// roles.  conv1 (5x5 on {0,1} planes) has its own kernel (k_tc_conv1m); the dense heads are in
+// net_heads_tc.cu.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "net.cuh"
@@ -28,21 +28,14 @@
 
 namespace a5 {
 
-constexpr int TC_HALO = 24;             // >= pitch + 1 for S <= 15, multiple of 8
+constexpr int TC_HALO = 24;             // largest slab halo: >= pitch + 1 for S <= 15, multiple of 8
 constexpr int TC_KS = 32;               // channels per slab
-constexpr int TC_WSTAGE_MAX = 2 * (TC_KS / 8) * 128 * 16;   // 16 KB (Cout = 128)
 constexpr int TC_EPI_WARPS = 16;        // four per TMEM lane quadrant
-constexpr int TC_W_WARP = 2 + TC_EPI_WARPS;   // weight-stage producer (its own warp: slab prefetch must not wait on weight-ring credits)
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;
-// T = M tiles (of 128 positions) per group; a group shares every weight stage.
+constexpr int TC_W_WARP = 2 + TC_EPI_WARPS;   // weight producer (its own warp: slab prefetch must not wait on weight-ring credits)
+// T = M tiles (of 128 positions) per CTA and group
 template <int T>
 struct TCfg {
   static constexpr int ROWS = T * 128;                 // positions per group
-  static constexpr int SROWS = ROWS + 2 * TC_HALO;     // staged positions per slab plane
-  static constexpr int PLANE = SROWS * 16;             // bytes per (kchunk) plane in smem
-  static constexpr int SLAB = 2 * (TC_KS / 8) * PLANE; // hi+lo, 4 kchunks
-  static constexpr int WSTAGES = T >= 4 ? 4 : 8;
-  static constexpr int SMEM = 2 * SLAB + WSTAGES * TC_WSTAGE_MAX + 128 * 4 + 256 + (32 * 16 + 16) * 4 + 128;
 };
 
 struct TCLayer {
@@ -311,185 +304,6 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
   }
 }
 
-// ------------------------------------------------------------------ the conv kernel
-template <int T>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant__ TCLayer L) {
-  using Cfg = TCfg<T>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* a_buf = smem;                                   // 2 slabs
-  uint8_t* w_buf = smem + 2 * Cfg::SLAB;                   // WSTAGES stages
-  float* s_bias = (float*)(w_buf + Cfg::WSTAGES * TC_WSTAGE_MAX);
-  TCBarriers* B = (TCBarriers*)(s_bias + 128);
-  float* s_hw = (float*)((uint8_t*)B + 256);              // head conv weights [32][head_ch], then bias * ACT_SCALE
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cout = L.cout;
-  const int cpt = L.fold ? 2 * cout : cout;                // TMEM columns per M tile
-  const int nbuf = (T * cpt <= 256) ? 2 : 1;               // TMEM accumulator buffers
-  const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
-  const int nslabs = main_slabs + res_slabs;
-  const uint32_t stage_bytes = 2u * (TC_KS / 8) * cout * 16u;
-
-  pdl_launch_dependents();
-  if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
-  if (L.head_ch) {
-    for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC_THREADS) s_hw[i] = L.head_w[i];
-    if (threadIdx.x < L.head_ch) s_hw[32 * 16 + threadIdx.x] = L.head_b[threadIdx.x] * ACT_SCALE;
-  }
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&B->a_full[i], 1); mbar_init(&B->a_empty[i], 1); }
-    for (int i = 0; i < Cfg::WSTAGES; ++i) { mbar_init(&B->w_full[i], 1); mbar_init(&B->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 1); mbar_init(&B->t_empty[i], TC_EPI_WARPS); }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = B->tmem_base;
-
-  if (warp == 0) {
-    // ===================== A producer: activation slabs HBM -> SMEM =====================
-    // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
-    int ab = 0, aph = 0, dn = 0;
-    pdl_wait();                                              // the layer(s) that wrote src / res are complete
-    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - TC_HALO;
-      for (int s = 0; s < nslabs; ++s) {
-        const bool is_res = s >= main_slabs;
-        const __half* X = is_res ? L.res : L.src;
-        const int xch = is_res ? L.res_ch : L.src_ch;
-        const int kc0 = (is_res ? s - main_slabs : s) * (TC_KS / 8);
-        mbar_wait(&B->a_empty[ab], aph ^ 1);
-        if (lane == 0) dbg_mark(L.dbg, 0, dn);             // slab load issued
-        if (elect_one()) {
-          mbar_expect_tx(&B->a_full[ab], Cfg::SLAB);
-          uint8_t* dst = a_buf + ab * Cfg::SLAB;
-#pragma unroll
-          for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-            for (int j = 0; j < TC_KS / 8; ++j) {
-              const __half* p = X + ((long long)(hl * (xch / 8) + kc0 + j) * L.plane_rows + r0) * 8;
-              bulk_g2s(dst + (hl * (TC_KS / 8) + j) * Cfg::PLANE, p, Cfg::PLANE, &B->a_full[ab]);
-            }
-        }
-        __syncwarp();
-        if (++ab == 2) { ab = 0; aph ^= 1; }
-      }
-    }
-  } else if (warp == TC_W_WARP) {
-    // ===================== W producer: weight stages L2 -> SMEM =====================
-    int ws = 0, wph = 0;
-    const int nstage = main_slabs * L.ntaps + res_slabs;
-    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-      const __half* wsrc = L.wpk;
-      for (int t = 0; t < nstage; ++t) {
-        mbar_wait(&B->w_empty[ws], wph ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&B->w_full[ws], stage_bytes);
-          bulk_g2s(w_buf + ws * TC_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
-        }
-        __syncwarp();
-        wsrc += stage_bytes / 2;
-        if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // Warp-uniform control flow (descriptor arithmetic stays in uniform registers); the
-    // tcgen05.mma / commit instructions themselves are issued by one elected lane.  The
-    // taps are unrolled with their shifts in registers so nothing but the barrier wait sits
-    // between the MMAs of consecutive stages.
-    const uint32_t idesc = instr_desc(128, cout), idesc2 = instr_desc(128, 2 * cout);
-    const uint32_t w_lbo = 2u * (uint32_t)cout * 16u;       // stage layout [kchunk][hi|lo][cout][8]
-    const bool fold = L.fold != 0;
-    // descriptor deltas (the start-address field counts 16-byte units)
-    constexpr uint64_t A_TILE = 128u * 16u / 16u;            // next M tile
-    constexpr uint64_t A_K16 = 2u * Cfg::PLANE / 16u;        // next 16 channels
-    constexpr uint64_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;  // hi -> lo planes
-    const uint64_t w_k16 = (uint64_t)(2u * w_lbo / 16u);
-    const uint64_t w_lo16 = (uint64_t)(cout * 16u / 16u);
-    const uint64_t ad_base = smem_desc(smem_u32(a_buf) + (uint32_t)TC_HALO * 16u, Cfg::PLANE, 128);
-    const uint64_t bd_base = smem_desc(smem_u32(w_buf), w_lbo, 128);
-    int sh[9];                                               // tap shifts, in rows (= 16-byte units)
-#pragma unroll
-    for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
-    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0, dn = 0, dn3 = 0;
-    for (int g = blockIdx.x; g < L.ngroups; g += gridDim.x) {
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: waiting for TMEM
-      mbar_wait(&B->t_empty[tb], tph ^ 1);
-      tc_fence_after();
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: TMEM free
-      const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt);
-      for (int s = 0; s < nslabs; ++s) {
-        const bool is_res = s >= main_slabs;
-        const int ntap = is_res ? 1 : L.ntaps;
-        mbar_wait(&B->a_full[ab], aph);
-        tc_fence_after();
-        if (lane == 0) dbg_mark(L.dbg, 1, dn);             // slab landed
-        const uint64_t ad_slab = ad_base + (uint64_t)(ab * (Cfg::SLAB / 16));
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          if (t < ntap) {
-            if (lane == 0) dbg_mark(L.dbg, 3, dn3);        // stage: waiting for weights
-            mbar_wait(&B->w_full[ws], wph);
-            tc_fence_after();
-            if (lane == 0) dbg_mark(L.dbg, 3, dn3);        // stage: weights landed
-            const uint64_t ad0 = ad_slab + (uint64_t)(int64_t)(is_res ? 0 : sh[t]);
-            const uint64_t bd0 = bd_base + (uint64_t)(ws * (TC_WSTAGE_MAX / 16));
-            const uint32_t first = (uint32_t)(s | t);
-            const bool last_tap = t == ntap - 1;
-            if (elect_one()) {
-              if (fold) {
-                // a_hi * [w_hi | w_lo] -> columns [0, 2 cout); a_lo * w_hi accumulates into [0, cout)
-#pragma unroll
-                for (int m = 0; m < T; ++m) {
-#pragma unroll
-                  for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, bd0 + k * w_k16, idesc2, (first | k) != 0);
-#pragma unroll
-                  for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, bd0 + k * w_k16, idesc, 1u);
-                }
-              } else {
-#pragma unroll
-                for (int m = 0; m < T; ++m) {
-#pragma unroll
-                  for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
-#pragma unroll
-                    for (int k = 0; k < TC_KS / 16; ++k)
-                      tc_mma(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0),
-                             bd0 + k * w_k16 + (pass == 2 ? w_lo16 : 0), idesc, (first | pass | k) != 0);
-                  }
-                }
-              }
-              tc_commit(&B->w_empty[ws]);                  // stage reusable once these MMAs retire
-              if (last_tap) tc_commit(&B->a_empty[ab]);
-              if (last_tap && s == nslabs - 1) tc_commit(&B->t_full[tb]);
-            }
-            __syncwarp();
-            if (++ws == Cfg::WSTAGES) { ws = 0; wph ^= 1; }
-          }
-        }
-        if (++ab == 2) { ab = 0; aph ^= 1; }
-      }
-      if (lane == 0) dbg_mark(L.dbg, 1, dn);               // group: all MMAs issued
-      if (++tb == nbuf) { tb = 0; tph ^= 1; }
-    }
-  } else {
-    tc_epilogue<T, false>(L, B, tmem, s_bias, s_hw, warp, lane, cpt, nbuf, blockIdx.x, L.ngroups, gridDim.x);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
-  }
-}
-
 // ------------------------------------------------------------------ the CTA-pair conv kernel
 // Same computation as k_tc_conv on a pair of SMs (cluster of 2, tcgen05 cta_group::2): one
 // tcgen05.mma covers M = 256 -- the T tiles of this CTA and the T tiles of its peer -- while the
@@ -515,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv(const __grid_constant
 // accumulators: no ordering between them is needed; every "empty"/"ready" barrier counts both
 // commits), and (ii) RESW: when the layer's whole weight set fits beside the slabs it is loaded once
 // per CTA and stays resident -- no per-stage wait / commit, and 1/16 of the L2 -> SMEM weight traffic.
-constexpr int TC2_THREADS = TC_THREADS + 32;
+constexpr int TC2_THREADS = 32 * (2 + TC_EPI_WARPS + 2);   // producer, issuer/relay, epilogue, W producer, 2nd issuer
 constexpr int TC2_MMA_WARP1 = TC_W_WARP + 1;              // second MMA issuer (leader CTA only)
 constexpr int TC2_WSTAGES = 8;
 constexpr int TC2_WSTAGE_MAX = 4 * 128 * 16;              // 8 KB (cout = 128: 64 + 64 rows)
@@ -525,13 +339,6 @@ constexpr int TC2_SMEM_LIMIT = 232448;                    // 227 KB opt-in maxim
 __device__ __forceinline__ void tc_commit2(uint64_t* bar) {   // arrive on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 
 // slab geometry of the pair kernel: the halo is a template parameter (>= pitch + 1, multiple of 8: 16 for
@@ -853,96 +660,6 @@ __global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ support kernels
-// conv1 (5x5, 3->32, ELU; network.py:63) from the int8 planes into the tensor-core activation
-// layout.  The inputs are {0,1} (utils.py:256-272), so a kernel row applied to a window row is
-// one of 32 possible partial sums: a table T[plane][ky][5-bit pattern][32 ch] is built in shared
-// memory once per (persistent) CTA, board rows are kept as bit masks, and every output is
-// bias + 15 table rows -- no multiplies, no data-dependent branches.
-constexpr int C1_THREADS = 256;
-constexpr int C1_NB = 4;                        // boards per CTA iteration
-constexpr int C1_SMEM = (15 * 32 * 32 + 75 * 32 + 32) * 4 + C1_NB * 3 * (A5_MAX_BOARD + 4) * 4;
-
-__global__ void __launch_bounds__(C1_THREADS) k_tc_conv1(const int8_t* __restrict__ planes, const float* __restrict__ W,
-                                                        const float* __restrict__ bias, __half* __restrict__ out,
-                                                        long long plane_rows, int S, int pitch, int per_board, int guard,
-                                                        int n) {
-  extern __shared__ __align__(16) float c1_smem[];
-  float* tab = c1_smem;                         // [3][5][32][32]
-  float* sw = tab + 15 * 32 * 32;               // [75][32] staging of the TF kernel
-  float* sb = sw + 75 * 32;
-  uint32_t (*rowmask)[3][A5_MAX_BOARD + 4] = (uint32_t (*)[3][A5_MAX_BOARD + 4])(sb + 32);
-  const int tid = threadIdx.x, C = S * S;
-  for (int i = tid; i < 75 * 32; i += C1_THREADS) sw[i] = W[(i / 32) * 64 + (i % 32)];   // packed ldw = 64
-  if (tid < 32) sb[tid] = bias[tid];
-  __syncthreads();
-  for (int i = tid; i < 15 * 32 * 32; i += C1_THREADS) {
-    const int pat = i & 31, ch = (i >> 5) & 31, pk = i >> 10;      // pk = p*5 + ky; [pk][ch][pat]: lanes differ in pat -> no bank conflicts
-    const int p = pk / 5, ky = pk - p * 5;
-    float acc = 0.0f;
-#pragma unroll
-    for (int kx = 0; kx < 5; ++kx)
-      if ((pat >> kx) & 1) acc += sw[((ky * 5 + kx) * 3 + p) * 32 + ch];
-    tab[i] = acc;
-  }
-  constexpr float K_L2E = 1.4426950408889634f;
-  for (int b0 = blockIdx.x * C1_NB; b0 < n; b0 += gridDim.x * C1_NB) {
-    __syncthreads();
-    for (int i = tid; i < C1_NB * 3 * (A5_MAX_BOARD + 4); i += C1_THREADS) ((uint32_t*)rowmask)[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < C1_NB * 3 * S; i += C1_THREADS) {   // one thread per (board, plane, row): bit (x + 2)
-      const int bb = i / (3 * S), pr = i - bb * 3 * S;
-      const int p = pr / S, y = pr - p * S;
-      if (b0 + bb < n) {
-        const int8_t* src = planes + (size_t)(b0 + bb) * 3 * C + p * C + y * S;
-        uint32_t m = 0;
-        for (int x = 0; x < S; ++x) m |= (src[x] != 0 ? 1u : 0u) << (x + 2);
-        rowmask[bb][p][y + 2] = m;
-      }
-    }
-    __syncthreads();
-    const int ppad = (per_board + 31) & ~31;     // lanes of a warp = 32 consecutive positions of one (board, chunk)
-    const int items = ppad * 4;
-    for (int i = tid; i < C1_NB * items; i += C1_THREADS) {
-      const int bb = i / items, it = i - bb * items;
-      const int kc = it / ppad, pos = it - kc * ppad;
-      if (b0 + bb >= n) break;
-      if (pos >= per_board) continue;
-      const int rr = pos / pitch, cc = pos - rr * pitch;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-      if (rr < S && cc < S) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = sb[kc * 8 + e];
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-          for (int ky = 0; ky < 5; ++ky) {
-            const uint32_t pat = (rowmask[bb][p][rr + ky] >> cc) & 31u;
-            const float* tp = &tab[((p * 5 + ky) * 32 + kc * 8) * 32 + pat];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += tp[e * 32];
-          }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : ex2_approx(v[e] * K_L2E) - 1.0f;
-      }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float x0 = v[2 * e] * ACT_SCALE, x1 = v[2 * e + 1] * ACT_SCALE;
-        const __half2 h = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-        hi[e] = *(const uint32_t*)&h;
-        lo[e] = *(const uint32_t*)&l;
-      }
-      const long long row = guard + (long long)(b0 + bb) * per_board + pos;
-      *(uint4*)(out + ((long long)kc * plane_rows + row) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *(uint4*)(out + ((long long)(4 + kc) * plane_rows + row) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------ conv1 on the tensor cores
 // conv1 (5x5, 3 -> 32, ELU; network.py:63) as a GEMM with an explicit A tile: the inputs are exactly
 // {0, 1} (utils.py:256-272), so A = im2col(planes) is exact in fp16 and only the weights are split:
@@ -1169,36 +886,6 @@ __global__ void k_c1m_pack(const float* __restrict__ w, int ldw, __half* __restr
   out[i] = (r >> 5) ? __float2half_rn(x - __half2float(h)) : h;
 }
 
-// TF kernel [taps][cin][cout] (+ optional res [1][rcin][cout]) -> per-(slab, tap) stages
-// [kchunk 4][hi|lo][cout][8] fp16, scaled by 2^10 (hi and lo adjacent along N, so one
-// N = 2*cout descriptor covers both).
-__global__ void k_tc_pack(const float* __restrict__ w, const float* __restrict__ wres, int ntaps, int cin, int rcin,
-                          int cout, __half* __restrict__ out) {
-  const int main_stages = (cin / TC_KS) * ntaps;
-  const int nstages = main_stages + (wres ? rcin / TC_KS : 0);
-  const long long per_stage = (long long)TC_KS * cout;
-  const long long total = (long long)nstages * per_stage;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int stage = (int)(i / per_stage);
-    const int r = (int)(i % per_stage);
-    const int j = r / (cout * 8), n = (r / 8) % cout, e = r % 8;
-    const int kin = j * 8 + e;
-    float x;
-    if (stage < main_stages) {
-      const int slab = stage / ntaps, tap = stage % ntaps;
-      x = w[((size_t)tap * cin + slab * TC_KS + kin) * cout + n];
-    } else {
-      const int slab = stage - main_stages;
-      x = wres[(size_t)(slab * TC_KS + kin) * cout + n];
-    }
-    x *= W_SCALE;
-    const __half h = __float2half_rn(x);
-    __half* base = out + (size_t)stage * 2 * per_stage;
-    base[(((size_t)j * 2 + 0) * cout + n) * 8 + e] = h;
-    base[(((size_t)j * 2 + 1) * cout + n) * 8 + e] = __float2half_rn(x - __half2float(h));
-  }
-}
-
 // TC activation (hi/lo fp16 planes) -> fp32 [row][ch]   (debug / parity tooling)
 __global__ void k_tc_unpack(const __half* __restrict__ x, int ch, long long plane_rows, long long nrows,
                             float* __restrict__ out) {
@@ -1229,8 +916,7 @@ static const TcLayerDef kTcLayers[11] = {
 
 struct a5_tc_state {
   __half* act[11] = {};
-  __half* wpk[11] = {};
-  __half* wpk2[11] = {};        // CTA-pair layout
+  __half* wpk2[11] = {};        // per layer: [stage][cta 2][kchunk 4][X rows | S rows][8]
   // block3-conv1 and block4-conv1 both read block2's output (network.py:68,79): the CTA-pair path
   // runs them as ONE layer of cout = 32 + 64 (N = 96 MMAs instead of N = 32/64 ones below the
   // ~44-cycle MMA floor, and the 128-channel input is read once)
@@ -1238,13 +924,11 @@ struct a5_tc_state {
   float* bias_m = nullptr;
   __half* wpk_c1 = nullptr;     // conv1 weights for k_tc_conv1m
   uint32_t* c1_bits = nullptr;  // bitboards of the input planes (k_c1_bits)
-  int conv1_tc = 1;             // A5_TC_CONV1=table: the CUDA-core table-lookup conv1
-  int cta2 = 1;                 // use k_tc_conv2 (A5_TC_CTA2=0 selects the single-CTA kernel)
   int resw = 1;                 // A5_TC_RESW=0: always stream weights through the stage ring
   int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
-  int t128 = 4, t64 = 2, fold = 1;
+  int fold = 1;
   int num_sms = 0;
   a5::HeadsState* heads = nullptr;
 };
@@ -1286,7 +970,6 @@ int tc_alloc(a5_net* net) {
   for (int l = 1; l <= 10; ++l) {
     const TcLayerDef& L = kTcLayers[l];
     size_t stages = (size_t)(L.cin / TC_KS) * 9 + (L.res_src >= 0 ? L.res_cin / TC_KS : 0);
-    A5_CUDA(cudaMalloc(&tc->wpk[l], stages * 2 * TC_KS * L.cout * sizeof(__half)));
     A5_CUDA(cudaMalloc(&tc->wpk2[l], stages * 2 * 4 * (L.cout + L.cout / 2) * 8 * sizeof(__half)));
   }
   A5_CUDA(cudaMalloc(&tc->wpk2_m, (size_t)(128 / TC_KS) * 9 * 2 * 4 * 96 * 8 * sizeof(__half)));
@@ -1294,22 +977,15 @@ int tc_alloc(a5_net* net) {
   A5_CUDA(cudaMalloc(&tc->wpk_c1, C1M_WBYTES));
   A5_CUDA(cudaMalloc(&tc->c1_bits, (size_t)net->max_batch * C1M_BW * sizeof(uint32_t)));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1m, cudaFuncAttributeMaxDynamicSharedMemorySize, C1M_SMEM));
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<4>::SMEM));
-  A5_CUDA(cudaFuncSetAttribute(k_tc_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<2>::SMEM));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
   const char* ev;
-  tc->t128 = ((ev = getenv("A5_TC_T128")) && atoi(ev) == 2) ? 2 : 4;
-  tc->t64 = ((ev = getenv("A5_TC_T64")) && atoi(ev) == 4) ? 4 : 2;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
-  tc->cta2 = ((ev = getenv("A5_TC_CTA2")) && atoi(ev) == 0) ? 0 : 1;
   tc->resw = ((ev = getenv("A5_TC_RESW")) && atoi(ev) == 0) ? 0 : 1;
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
-  tc->conv1_tc = ((ev = getenv("A5_TC_CONV1")) && !strcmp(ev, "table")) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
@@ -1322,7 +998,6 @@ int tc_alloc(a5_net* net) {
 void tc_free(a5_net* net) {
   if (!net->tc) return;
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->act[i]);
-  for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk[i]);
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk2[i]);
   cudaFree(net->tc->wpk2_m);
   cudaFree(net->tc->bias_m);
@@ -1340,8 +1015,6 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     const int t0 = kBlocks[(l - 1) / 2].t0;
     const float* w = (l & 1) ? t[t0 + 2] : t[t0 + 4];
     const float* wres = (l & 1) ? nullptr : t[t0 + 0];
-    k_tc_pack<<<256, 256, 0, st>>>(w, wres, 9, L.cin, L.res_cin, L.cout, tc->wpk[l]);
-    A5_CUDA(cudaGetLastError());
     k_tc_pack2<<<256, 256, 0, st>>>(w, nullptr, 0, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
     A5_CUDA(cudaGetLastError());
   }
@@ -1366,18 +1039,13 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   PosSpace ps(net->S);
   TC_MARK(0);
   const long long nrows1 = (long long)n * ps.per_board;
-  if (tc->conv1_tc) {
+  {
     const int ntiles = (int)((nrows1 + 127) / 128);
     const int grid1 = ntiles < 2 * tc->num_sms ? ntiles : 2 * tc->num_sms;
     k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits);
     A5_CUDA(cudaGetLastError());
     k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
                                                      ps.pitch, ps.per_board, ps.guard, n, ntiles);
-  } else {
-    const int nb1 = (n + C1_NB - 1) / C1_NB;
-    const int grid1 = nb1 < 3 * tc->num_sms ? nb1 : 3 * tc->num_sms;
-    k_tc_conv1<<<grid1, C1_THREADS, C1_SMEM, st>>>(planes, net->w[0], net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
-                                     ps.per_board, ps.guard, n);
   }
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
@@ -1386,12 +1054,11 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     TcLayerDef D = kTcLayers[l];
     TCLayer L;
     memset(&L, 0, sizeof(L));
-    const bool merged = tc->cta2 && tc->merge && l == 5;      // block3-conv1 + block4-conv1 as one cout = 96 layer
-    if (tc->cta2 && tc->merge && l == 7) { TC_MARK(1 + l); continue; }
+    const bool merged = tc->merge && l == 5;      // block3-conv1 + block4-conv1 as one cout = 96 layer
+    if (tc->merge && l == 7) { TC_MARK(1 + l); continue; }
     if (merged) D.cout = 96;
     L.src = tc->act[D.src]; L.src_ch = D.cin;
     L.res = D.res_src >= 0 ? tc->act[D.res_src] : nullptr; L.res_ch = D.res_cin;
-    L.wpk = tc->wpk[l];
     L.bias = net->bias[l];
     L.out = tc->act[D.out];
     L.out_f32 = nullptr;
@@ -1413,7 +1080,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
-    if (tc->cta2) {
+    {
       // CTA pairs: T = 2 tiles per CTA, 4 per weight stage; TMEM double-buffers for every layer
       constexpr int T = 2;
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
@@ -1440,13 +1107,6 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
       else if (h16) A5_CUDA(launch_pdl(k_tc_conv2<T, false, 16>, grid, TC2_THREADS, smem, st, L, tc->pdl));
       else if (resw) A5_CUDA(launch_pdl(k_tc_conv2<T, true, 24>, grid, TC2_THREADS, smem, st, L, tc->pdl));
       else A5_CUDA(launch_pdl(k_tc_conv2<T, false, 24>, grid, TC2_THREADS, smem, st, L, tc->pdl));
-    } else {
-      const int T = (D.cout == 128) ? tc->t128 : (D.cout == 64 ? tc->t64 : 4);
-      const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
-      L.ngroups = ngroups;
-      int grid = ngroups < tc->num_sms ? ngroups : tc->num_sms;
-      if (T == 4) A5_CUDA(launch_pdl(k_tc_conv<4>, grid, TC_THREADS, TCfg<4>::SMEM, st, L, tc->pdl));
-      else A5_CUDA(launch_pdl(k_tc_conv<2>, grid, TC_THREADS, TCfg<2>::SMEM, st, L, tc->pdl));
     }
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
