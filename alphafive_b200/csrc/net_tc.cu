@@ -48,6 +48,9 @@ struct TCLayer {
   float* out_f32;
   int cout, ntaps;
   int fold;                      // 1: hi*[Whi|Wlo] as one N = 2*cout MMA (cout <= 64)
+  int reverse;                   // 1: walk the groups from the last to the first.  Layers alternate direction so
+                                 // that each starts on the rows its predecessor touched last: ~100 MB of every
+                                 // 150-450 MB activation tensor are then still in the 126 MB L2
   int nslab_buf, w_bytes;        // pair kernel: A slab buffers, bytes of the weight region (ring or resident set)
   unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
   // fused 1x1 head conv + ELU in the epilogue (network.py:69-70 value, :81-82 policy): the
@@ -125,7 +128,7 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
       constexpr int NPART = (TC_EPI_WARPS / 4) / T > 0 ? (TC_EPI_WARPS / 4) / T : 1;
       const int part = sub / T;
       for (int m = sub % T; m < T && (part == 0 || L.head_ch == 16); m += T * NPART) {
-        const uint32_t q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;
+        const uint32_t q = (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS + m * 128 + quad * 32 + lane;
         const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
         const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
         const bool real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
@@ -231,7 +234,7 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
       const int m = u / nc, c0 = (u - m * nc) << 4;
       if (m != cur_m) {
         cur_m = m;
-        q = (uint32_t)g * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
+        q = (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
         const uint32_t within = q % (uint32_t)L.per_board;
         const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
         real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
@@ -434,7 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     int ab = 0, aph = 0, dn = 0;
     pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = g_first; g < g_end; g += g_step) {
-      const long long r0 = L.row0 + (long long)g * Cfg::ROWS - HALO;
+      const long long r0 = L.row0 + (long long)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS - HALO;
       SlabSeq seq(main_slabs, res_slabs);
       for (int s = 0; s < nslabs; ++s) {
         int sidx;
@@ -924,6 +927,7 @@ struct a5_tc_state {
   float* bias_m = nullptr;
   __half* wpk_c1 = nullptr;     // conv1 weights for k_tc_conv1m
   uint32_t* c1_bits = nullptr;  // bitboards of the input planes (k_c1_bits)
+  int zigzag = 1;               // A5_TC_ZIGZAG=0: every layer walks the groups in ascending order
   int resw = 1;                 // A5_TC_RESW=0: always stream weights through the stage ring
   int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
@@ -984,6 +988,7 @@ int tc_alloc(a5_net* net) {
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
   const char* ev;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
+  tc->zigzag = ((ev = getenv("A5_TC_ZIGZAG")) && atoi(ev) == 0) ? 0 : 1;
   tc->resw = ((ev = getenv("A5_TC_RESW")) && atoi(ev) == 0) ? 0 : 1;
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
@@ -1077,6 +1082,8 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
     L.fold = (D.cout <= 64) ? tc->fold : 0;
+    // conv1 writes ascending; from there on every layer starts where its inputs were touched last
+    L.reverse = tc->zigzag && (l == 1 || l == 3 || l == 5 || l == 8 || l == 10);
     L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;

@@ -321,7 +321,7 @@ def run_ours(a):
             "moves": moves, "sims_run": nsims, "games_finished": games, "records_per_step": recs / max(1, a.steps),
             "clocks": clocks,
         }
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
             cores = max(1, min((os.cpu_count() or 1) - 1, 64))
             v, ev, wall = cpu_moves_per_sec(S, sims, upper, cores, 2)
             v5, ev5, _ = cpu_moves_per_sec(S, sims, upper, min(5, cores), 2)     # config.py:20 max_processes = 5
