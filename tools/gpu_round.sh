@@ -3,6 +3,7 @@ T=${1:-r01b}
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${T}_pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.log 2>&1
 timeout 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 timeout 300 python tools/layer_times.py 11 4096 20 > gpurun_out/${T}_layers.txt 2>&1
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err
