@@ -1,7 +1,10 @@
-"""TensorFlow checkpoint-v2 ("bundle") reader, without TensorFlow.
+"""TensorFlow checkpoint-v2 ("bundle") reader and writer, without TensorFlow.
 
-Replaces the loading half of the reference's ``ResNet.restore``
-(genData/network.py:113-122), whose only implementation is ``tf.train.Saver``.
+Replaces the reference's ``ResNet.restore`` (genData/network.py:113-122) and the
+``net.saver.save`` calls of its trainer (main.py:74-77), whose only implementation is
+``tf.train.Saver``: ``read_bundle`` loads the shipped checkpoints, ``write_bundle`` writes
+files the reference's ``restore`` can load (for the 42 variables of ckpt/alphaFive-6960 it
+reproduces the shipped ``.index`` and ``.data`` files byte for byte -- tests/test_ckpt.py).
 A bundle is ``<prefix>.index`` -- a LevelDB table whose values are
 ``BundleEntryProto`` messages -- plus ``<prefix>.data-00000-of-00001`` holding
 the raw little-endian tensors.  Only what the shipped checkpoints use is
@@ -138,3 +141,122 @@ def read_bundle(path: str) -> dict[str, np.ndarray]:
             arr = np.frombuffer(bytes(data[toff:toff + tsize]), dtype="<f4").reshape(shape)
             out[key.decode()] = arr.astype(np.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# writer
+# ---------------------------------------------------------------------------------------
+def _crc32c_table():
+    tab = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tab.append(c)
+    return tab
+
+
+_CRC_TAB = None
+
+
+def crc32c(data: bytes) -> int:
+    """CRC-32C (Castagnoli), the checksum of LevelDB tables and bundle entries.  Slicing-by-8 over
+    numpy for the 3 MB tensor file would be faster; one checkpoint per 60 steps does not need it."""
+    global _CRC_TAB
+    if _CRC_TAB is None:
+        _CRC_TAB = _crc32c_table()
+    tab = _CRC_TAB
+    c = 0xFFFFFFFF
+    for b in data:
+        c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def _masked_crc(data: bytes) -> int:
+    c = crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def _put_varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _build_block(entries, restart_interval=16) -> bytes:
+    """LevelDB block: prefix-compressed (key, value) entries + restart array + restart count."""
+    out, restarts, last, n = bytearray(), [], b"", 0
+    for key, val in entries:
+        shared = 0
+        if n % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            while shared < min(len(last), len(key)) and last[shared] == key[shared]:
+                shared += 1
+        out += _put_varint(shared) + _put_varint(len(key) - shared) + _put_varint(len(val)) + key[shared:] + val
+        last, n = key, n + 1
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        out += struct.pack("<I", r)
+    out += struct.pack("<I", len(restarts))
+    return bytes(out)
+
+
+def _entry_proto(shape, offset: int, size: int, crc: int) -> bytes:
+    """BundleEntryProto: dtype DT_FLOAT, shape, (offset), size, crc32c (masked, fixed32)."""
+    dims = b"".join(b"\x12" + _put_varint(len(d)) + d for d in (b"\x08" + _put_varint(int(n)) for n in shape))
+    out = b"\x08\x01" + b"\x12" + _put_varint(len(dims)) + dims
+    if offset:
+        out += b"\x20" + _put_varint(offset)
+    out += b"\x28" + _put_varint(size) + b"\x35" + struct.pack("<I", crc)
+    return out
+
+
+def _short_successor(key: bytes) -> bytes:
+    """leveldb BytewiseComparator::FindShortSuccessor: first byte that can be incremented, truncated there."""
+    for i, b in enumerate(key):
+        if b != 0xFF:
+            return key[:i] + bytes([b + 1])
+    return key
+
+
+def write_bundle(prefix: str, tensors: dict, update_marker: bool = True) -> None:
+    """Write ``<prefix>.index`` and ``<prefix>.data-00000-of-00001`` (and the directory's ``checkpoint``
+    marker) for float32 ``tensors`` in TF layout, as ``tf.train.Saver.save`` lays a one-shard bundle out:
+    tensors concatenated in key order, one table block of BundleEntryProto values (restart interval 16),
+    an empty metaindex block, a one-entry index block, and the 48-byte footer."""
+    names = sorted(tensors)
+    data = bytearray()
+    entries = [(b"", b"\x08\x01\x1a\x02\x08\x01")]              # BundleHeaderProto: num_shards 1, version.producer 1
+    for name in names:
+        arr = np.asarray(tensors[name], dtype="<f4")
+        raw = arr.tobytes(order="C")
+        entries.append((name.encode(), _entry_proto(arr.shape, len(data), len(raw), _masked_crc(raw))))
+        data += raw
+
+    def with_trailer(block: bytes) -> bytes:
+        return block + b"\x00" + struct.pack("<I", _masked_crc(block + b"\x00"))
+
+    data_block = _build_block(entries)
+    meta_block = _build_block([])
+    out = bytearray(with_trailer(data_block))
+    meta_off = len(out)
+    out += with_trailer(meta_block)
+    index_block = _build_block([(_short_successor(names[-1].encode()), _put_varint(0) + _put_varint(len(data_block)))], 1)
+    index_off = len(out)
+    out += with_trailer(index_block)
+    footer = _put_varint(meta_off) + _put_varint(len(meta_block)) + _put_varint(index_off) + _put_varint(len(index_block))
+    out += footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", _TABLE_MAGIC)
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    with open(prefix + ".data-00000-of-00001", "wb") as f:
+        f.write(bytes(data))
+    with open(prefix + ".index", "wb") as f:
+        f.write(bytes(out))
+    if update_marker:
+        base = os.path.basename(prefix)
+        with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
+            f.write(f'model_checkpoint_path: "{base}"\nall_model_checkpoint_paths: "{base}"\n')

@@ -121,7 +121,8 @@ def train_loop(config, n_games=4096, total_step=None, restore=None, seed=0, save
                 step += 1
                 log("step: %d, xcross_loss: %0.3f, mse: %0.3f, entropy: %0.3f" % (step, *out))
                 if save_dir and step % save_every == 0:
-                    np.savez(f"{save_dir}/alphaFive-{step}.npz", **{k.replace("/", "__"): v for k, v in trainer.weights().items()})
+                    trainer.sync_to(net)
+                    net.save(f"{save_dir}/alphaFive", global_step=step)       # main.py:74
                     stack.save(step, directory=save_dir)
         trainer.sync_to(net)
     return trainer, stack, step

@@ -80,6 +80,14 @@ class ResNet(object):
         for v in missed:
             print(v)
 
+    def save(self, save_path, global_step=None):
+        """``self.saver.save(self.sess, save_path=..., global_step=...)`` (main.py:74-77): a TF checkpoint-v2
+        bundle ``<save_path>-<step>.{index,data-00000-of-00001}`` + the ``checkpoint`` marker, loadable by
+        the reference's ``restore`` (no ``.meta``: the reference rebuilds the graph in code)."""
+        prefix = save_path if global_step is None else f"{save_path}-{global_step}"
+        ckpt.write_bundle(prefix, {k: v.cpu().numpy() for k, v in self.device_net.params.items()})
+        return prefix
+
     def set_weights(self, weights: dict):
         self.device_net.set_weights({k: np.asarray(v, np.float32) for k, v in weights.items()})
 

@@ -16,6 +16,7 @@ mcts_game_{S}.npz    a multi-move deterministic game with tree reuse (budget rul
 mcts_train_11.npz    seeded training-mode summary statistics (distributional pins)
 replay_sample.npz    1,024 records + 3 whole games of data_buffer/data6960.pkl
 ckpt6960.npz         the 42 tensors of ckpt/alphaFive-6960 (via alphafive_b200.ckpt)
+ckpt6960_files.npz   the shipped .index file verbatim + sha256 of the .data file (pins the writer)
 weights.npz          construct_weights(L, 0.94) for L = 1..64
 replay_stack.npz     utils.RandomStack driven with seeded generators: accept flags and
                      bookkeeping after every push, one get_data batch
@@ -278,9 +279,15 @@ def make_replay(utils):
 
 
 def make_ckpt():
+    import hashlib
     from alphafive_b200 import ckpt
     w = ckpt.read_bundle(f"{REF}/ckpt")
     np.savez_compressed(os.path.join(OUT, "ckpt6960.npz"), **{k.replace("/", "__"): v for k, v in w.items()})
+    # the shipped files themselves, to pin the bundle *writer*: the 1.7 KB index verbatim, the 3 MB data file by hash
+    np.savez_compressed(os.path.join(OUT, "ckpt6960_files.npz"),
+                        index=np.frombuffer(open(f"{REF}/ckpt/alphaFive-6960.index", "rb").read(), np.uint8),
+                        data_sha256=hashlib.sha256(open(f"{REF}/ckpt/alphaFive-6960.data-00000-of-00001", "rb").read()).hexdigest(),
+                        marker=open(f"{REF}/ckpt/checkpoint").read())
     print("ckpt6960:", len(w), "tensors", sum(v.size for v in w.values()), "params")
 
 
@@ -336,6 +343,9 @@ def make_replay_stack(utils):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--ckpt-only" in sys.argv:
+        make_ckpt()
+        return
     if "--replay-stack-only" in sys.argv:
         make_replay_stack(_ref()[0])
         return

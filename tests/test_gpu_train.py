@@ -90,4 +90,7 @@ def test_train_loop_driver(cuda_lib, tmp_path):
                                       passes_per_poll=60, log=lines.append)
     assert step == 4 and trainer.t == 12 and stack.is_full() and len(lines) == 3
     assert lines[0].startswith("step: 2, xcross_loss: ")
-    assert (tmp_path / "alphaFive-2.npz").exists() and (tmp_path / "data2.pkl").exists()
+    assert (tmp_path / "alphaFive-2.index").exists() and (tmp_path / "data2.pkl").exists()
+    from alphafive_b200 import ckpt
+    back = ckpt.read_bundle(str(tmp_path))                     # resolves through the `checkpoint` marker
+    assert set(back) == set(trainer.weights()) and back["policy/fc/kernel"].shape == (16 * 121, 121)
