@@ -66,6 +66,8 @@ _SIGS = {
     "a5_engine_root_stats": (_I, [_P, _P, _P, _P, _P, _P]),
     "a5_engine_table_dump": (_I, [_P, _I, _P, _P, _I, C.POINTER(C.c_int32), _P]),
     "a5_record_stride": (_I, [_I]),
+    "a5_net_forward_parts": (_I, [_P, _P, _I, _P, _P, _I, _P]),
+    "a5_net_set_sm_limit": (_I, [_P, _I, _I]),
     "a5_replay_sample": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "a5_engine_harvest": (_I, [_P, _P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "a5_engine_counters": (_I, [_P, C.POINTER(C.c_int64), _P]),

@@ -43,5 +43,5 @@ HeadsIO heads_io(const HeadsState* h);
 int tc_alloc(a5_net* net);
 void tc_free(a5_net* net);
 int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st);
-int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st);
+int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st, int parts = 7);
 }  // namespace a5

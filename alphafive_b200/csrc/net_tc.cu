@@ -933,7 +933,8 @@ struct a5_tc_state {
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
   int fold = 1;
-  int num_sms = 0;
+  int num_sms = 0;               // SMs the block convs may use (one persistent CTA each)
+  int front_sms = 0;             // SMs conv1 may use (a5_net_set_sm_limit: SM-partitioned streams)
   a5::HeadsState* heads = nullptr;
 };
 
@@ -997,6 +998,7 @@ int tc_alloc(a5_net* net) {
   int dev = 0;
   A5_CUDA(cudaGetDevice(&dev));
   A5_CUDA(cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  tc->front_sms = tc->num_sms;
   return A5_OK;
 }
 
@@ -1039,14 +1041,14 @@ static unsigned long long* g_tc_dbg = nullptr;   // a5__debug_timeline: [10 laye
 #define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
 
 // heads + biases come from the fp32 path's packed copies (fp32_set_weights runs first)
-int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st) {
+int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st, int parts) {
   a5_tc_state* tc = net->tc;
   PosSpace ps(net->S);
   TC_MARK(0);
   const long long nrows1 = (long long)n * ps.per_board;
-  {
+  if (parts & A5_NET_PART_FRONT) {
     const int ntiles = (int)((nrows1 + 127) / 128);
-    const int grid1 = ntiles < 2 * tc->num_sms ? ntiles : 2 * tc->num_sms;
+    const int grid1 = ntiles < 2 * tc->front_sms ? ntiles : 2 * tc->front_sms;
     k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits);
     A5_CUDA(cudaGetLastError());
     k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
@@ -1055,7 +1057,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
-  for (int l = 1; l <= 10; ++l) {
+  for (int l = 1; l <= 10 && (parts & A5_NET_PART_BODY); ++l) {
     TcLayerDef D = kTcLayers[l];
     TCLayer L;
     memset(&L, 0, sizeof(L));
@@ -1118,7 +1120,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
   }
-  int rc = heads_forward(net, tc->heads, n, prob, value, st);
+  int rc = (parts & A5_NET_PART_HEADS) ? heads_forward(net, tc->heads, n, prob, value, st) : A5_OK;
   TC_MARK(12);
   return rc;
 }
@@ -1127,6 +1129,24 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
 
 extern "C" {
 int a5_net_tc_available(void) { return 1; }
+
+int a5_net_set_sm_limit(a5_net* net, int body_sms, int front_sms) {
+  A5_ARG(net && net->tc && body_sms >= 2 && front_sms >= 1);
+  int dev = 0, total = 0;
+  A5_CUDA(cudaGetDevice(&dev));
+  A5_CUDA(cudaDeviceGetAttribute(&total, cudaDevAttrMultiProcessorCount, dev));
+  net->tc->num_sms = body_sms < total ? body_sms : total;
+  net->tc->front_sms = front_sms < total ? front_sms : total;
+  return A5_OK;
+}
+
+int a5_net_forward_parts(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value, int parts, void* stream) {
+  A5_ARG(net && net->tc && d_planes && n >= 0 && n <= net->max_batch && (parts & ~A5_NET_PART_ALL) == 0);
+  A5_ARG(!(parts & A5_NET_PART_HEADS) || (d_prob && d_value));
+  if (!net->has_weights) { set_error("a5_net_forward_parts: no weights set"); return A5_ERR_STATE; }
+  if (n == 0 || parts == 0) return A5_OK;
+  return tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream, parts);
+}
 
 // internal tooling: also store the block3 / block5 activations (normally consumed in-register by
 // the fused head convs) so a5__debug_activation can show them.
@@ -1139,7 +1159,7 @@ int a5__debug_timeline(a5_net* net, const int8_t* d_planes, int n, float* d_prob
                        unsigned long long* d_dbg, void* stream) {
   A5_ARG(net && d_planes && d_dbg);
   g_tc_dbg = d_dbg;
-  int rc = tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream);
+  int rc = tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream, A5_NET_PART_ALL);
   g_tc_dbg = nullptr;
   return rc;
 }
@@ -1155,7 +1175,7 @@ int a5__debug_layer_times(a5_net* net, const int8_t* d_planes, int n, int reps, 
   for (int i = 0; i < 12; ++i) h_ms[i] = 0.0f;
   for (int r = 0; r < reps; ++r) {
     g_tc_events = ev;
-    int rc = tc_forward(net, d_planes, n, d_prob, d_value, st);
+    int rc = tc_forward(net, d_planes, n, d_prob, d_value, st, A5_NET_PART_ALL);
     g_tc_events = nullptr;
     if (rc) return rc;
     A5_CUDA(cudaStreamSynchronize(st));

@@ -23,12 +23,12 @@ from .net import DeviceNet
 
 class SelfPlay:
     def __init__(self, cfg=None, n_games=4096, net: DeviceNet | None = None, training=True, seed=0,
-                 game_id_base=0, use_graph=True, **cfg_kw):
+                 game_id_base=0, use_graph=True, _defer_net=False, **cfg_kw):
         self.config = make_config(cfg, n_games=n_games, training=training, auto_play=True, seed=seed,
                                   game_id_base=game_id_base, **cfg_kw)
         self.engine = SearchEngine(self.config)
         self.N, self.S = n_games, self.config.board_size
-        self.net = net if net is not None else DeviceNet(self.S, n_games)
+        self.net = net if (net is not None or _defer_net) else DeviceNet(self.S, n_games)
         dev = self.engine.device
         self.prob = torch.zeros((n_games, self.S * self.S), dtype=torch.float32, device=dev)
         self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
@@ -101,6 +101,80 @@ class SelfPlay:
         return self.engine.counters()
 
 
+class PipelinedSelfPlay:
+    """``SelfPlay`` as two half batches on SM-partitioned streams (alphafive_b200.pipeline): the same games,
+    records and counters -- game g of the first half is global game ``game_id_base + g``, of the second
+    ``game_id_base + n_games / 2 + g`` -- with heads / tree pass / conv1 of one half hidden behind the block
+    convs of the other."""
+
+    def __init__(self, cfg=None, n_games=4096, weights=None, training=True, seed=0, game_id_base=0, small_sms=16,
+                 **cfg_kw):
+        from .net import glorot_init
+        from .pipeline import SmPartition, TwoHalfPipeline
+        assert n_games % 2 == 0
+        self.N, h = n_games, n_games // 2
+        cfg_kw.setdefault("max_inner", 2 if n_games >= 256 else 16)      # the engine's default for the whole batch
+        self.halves = [SelfPlay(cfg, n_games=h, net=None, training=training, seed=seed, game_id_base=game_id_base + i * h,
+                                use_graph=False, _defer_net=True, **cfg_kw) for i in (0, 1)]
+        self.config, self.S = self.halves[0].config, self.halves[0].S
+        w = weights if weights is not None else glorot_init(self.S, 0)
+        self.nets = [DeviceNet(self.S, h, w) for _ in (0, 1)]
+        for sp, net in zip(self.halves, self.nets):
+            sp.net = net
+        self.pipe = TwoHalfPipeline([sp.engine for sp in self.halves], self.nets, SmPartition.get(small_sms))
+        self.record_buf = torch.empty((sum(sp.record_buf.shape[0] for sp in self.halves), self.halves[0].engine.record_stride),
+                                      dtype=torch.uint8, device=self.halves[0].engine.device)
+        self.passes = 0
+
+    def set_weights(self, weights):
+        self.pipe.drain()
+        torch.cuda.current_stream().synchronize()
+        for n in self.nets:
+            n.set_weights(weights)
+
+    def start(self):
+        if not self.pipe.primed:
+            self.pipe.prime()
+
+    def set_budget(self, sims: int, upper: int):
+        self.pipe.drain()
+        for sp in self.halves:
+            sp.engine.set_budget(sims, upper)
+        for st in (self.pipe.part.small, self.pipe.part.big):
+            st.wait_stream(torch.cuda.current_stream())
+
+    def run_passes(self, k: int):
+        self.start()
+        self.pipe.run(k)
+        self.passes += k
+
+    def harvest(self):
+        self.pipe.drain()
+        n = g = 0
+        for sp in self.halves:
+            buf, games = sp.engine.harvest(sp.record_buf)
+            self.record_buf[n:n + buf.shape[0]] = buf
+            n += buf.shape[0]
+            g += games
+        for st in (self.pipe.part.small, self.pipe.part.big):       # the next passes must see the reset arenas
+            st.wait_stream(torch.cuda.current_stream())
+        return self.record_buf[:n], g
+
+    def harvest_games(self):
+        buf, _ = self.harvest()
+        return records_to_games(parse_records(buf, self.S), self.S)
+
+    def harvest_all_ranks(self, group=None):
+        buf, _ = self.harvest()
+        return gather_records(buf, group=group)
+
+    def counters(self):
+        self.pipe.drain()
+        torch.cuda.current_stream().synchronize()
+        a, b = (sp.engine.counters() for sp in self.halves)
+        return {k: (max(a[k], b[k]) if k in ("max_nodes", "passes") else a[k] + b[k]) for k in a}
+
+
 class BatchedPlayer:
     """N reference ``Player`` objects in lock-step, host buffers in and out."""
 
@@ -144,6 +218,70 @@ class BatchedPlayer:
             self.h_codes.copy_(codes, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         pol = self.h_policy.numpy().reshape(self.N, self.S, self.S)
+        if advance:
+            return pol, self.h_action.numpy(), self.h_next.numpy(), self.h_codes.numpy()
+        return pol, self.h_action.numpy()
+
+
+class PipelinedBatchedPlayer(BatchedPlayer):
+    """``BatchedPlayer`` with the search of the two halves of the batch pipelined on SM-partitioned streams
+    (alphafive_b200.pipeline); same call, same host buffers, same results."""
+
+    def __init__(self, cfg=None, n_players=2, weights=None, training=True, random_a=False, seed=0, game_id_base=0,
+                 small_sms=16, **cfg_kw):
+        from .net import glorot_init
+        from .pipeline import SmPartition, TwoHalfPipeline
+        assert n_players % 2 == 0
+        cfg_kw.setdefault("max_inner", 2 if n_players >= 256 else 16)
+        h = n_players // 2
+        self.config = make_config(cfg, n_games=h, training=training, random_a=random_a, auto_play=False, seed=seed,
+                                  game_id_base=game_id_base, **cfg_kw)
+        self.N, self.S = n_players, self.config.board_size
+        self.C = self.S * self.S
+        self.engines = [SearchEngine(make_config(cfg, n_games=h, training=training, random_a=random_a, auto_play=False,
+                                                 seed=seed, game_id_base=game_id_base + i * h, **cfg_kw)) for i in (0, 1)]
+        w = weights if weights is not None else glorot_init(self.S, 0)
+        self.nets = [DeviceNet(self.S, h, w) for _ in (0, 1)]
+        self.pipe = TwoHalfPipeline(self.engines, self.nets, SmPartition.get(small_sms))
+        dev = self.engines[0].device
+        N, S, C = self.N, self.S, self.C
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+        self.h_boards, self.h_last = pin(N, S, S, dtype=torch.int8), pin(N, dtype=torch.int32)
+        self.h_policy, self.h_action = pin(N, C, dtype=torch.float32), pin(N, dtype=torch.int32)
+        self.h_next, self.h_codes = pin(N, S, S, dtype=torch.int8), pin(N, dtype=torch.int8)
+        self.d_boards = torch.empty((N, S, S), dtype=torch.int8, device=dev)
+        self.d_last = torch.empty((N,), dtype=torch.int32, device=dev)
+        self.h2d_bytes = N * C + 4 * N
+        self.d2h_bytes = N * C * 4 + 4 * N + N * C + N
+
+    def get_actions(self, boards, last, active=None, clear=None, advance=False):
+        N, h = self.N, self.N // 2
+        self.h_boards.copy_(torch.as_tensor(boards, dtype=torch.int8).reshape(N, self.S, self.S))
+        self.h_last.copy_(torch.as_tensor(last, dtype=torch.int32))
+        self.d_boards.copy_(self.h_boards, non_blocking=True)
+        self.d_last.copy_(self.h_last, non_blocking=True)
+        half = lambda a, i: None if a is None else np.asarray(a)[i * h:(i + 1) * h]
+        for i, e in enumerate(self.engines):
+            e.set_roots(self.d_boards[i * h:(i + 1) * h], self.d_last[i * h:(i + 1) * h], half(active, i), half(clear, i))
+        left = max(1, max(int(e.sims_left().max().item()) for e in self.engines))
+        self.pipe.prime()
+        while True:
+            self.pipe.run(left)
+            self.pipe.drain()
+            if sum(e.busy() for e in self.engines) == 0:
+                break
+            left = max(1, max(int(e.sims_left().max().item()) for e in self.engines))
+        outs = [e.finish_move() for e in self.engines]
+        policy, action = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+        self.h_policy.copy_(policy, non_blocking=True)
+        self.h_action.copy_(action, non_blocking=True)
+        if advance:
+            nxt = rules.step(self.d_boards, action.clamp(min=0))
+            codes = rules.terminal(nxt, self.config.goal)
+            self.h_next.copy_(nxt, non_blocking=True)
+            self.h_codes.copy_(codes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        pol = self.h_policy.numpy().reshape(N, self.S, self.S)
         if advance:
             return pol, self.h_action.numpy(), self.h_next.numpy(), self.h_codes.numpy()
         return pol, self.h_action.numpy()

@@ -215,6 +215,18 @@ int a5_net_set_weights(a5_net* net, const float* const* d_tensors, void* stream)
 int a5_net_forward(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value,
                    int mode, void* stream);
 
+/* The tensor-core forward in three stream-ordered parts, for callers that pipeline two half batches on
+ * SM-partitioned streams (CUDA green contexts): FRONT = input bitboards + conv1, BODY = the nine block
+ * convolutions, HEADS = dense heads (writes d_prob / d_value).  a5_net_forward == all three on one stream.
+ * a5_net_set_sm_limit tells the persistent kernels how many SMs the stream they will run on owns. */
+#define A5_NET_PART_FRONT 1
+#define A5_NET_PART_BODY  2
+#define A5_NET_PART_HEADS 4
+#define A5_NET_PART_ALL   7
+int a5_net_forward_parts(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value, int parts, void* stream);
+int a5_net_set_sm_limit(a5_net* net, int body_sms, int front_sms);
+
+
 #ifdef __cplusplus
 }
 #endif
