@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--preroll-sims", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="two half batches pipelined on SM-partitioned streams (CUDA green contexts) instead of the "
+                         "single-stream CUDA-graph replay; bit-identical results, measured no faster on a power-capped "
+                         "B200 (DESIGN.md section 8)")
+    ap.add_argument("--small-sms", type=int, default=16, help="SMs of the small partition of the pipeline")
     return ap.parse_args()
 
 
@@ -172,7 +177,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import ctypes as ct
     from alphafive_b200 import _lib
+    from alphafive_b200._lib import check, ptr, stream_ptr
     from alphafive_b200.net import DeviceNet, glorot_init
     from alphafive_b200.selfplay import BatchedPlayer, SelfPlay
 
@@ -182,10 +189,28 @@ def run_ours(a):
     mode = {"fp32": _lib.NET_FP32, "tc": _lib.NET_TC}.get(a.net_mode)
     if mode is None:
         mode = _lib.NET_TC if getattr(lib, "a5_net_tc_available", lambda: 0)() else _lib.NET_FP32
-    net = DeviceNet(S, N, glorot_init(S, 0), mode=mode)
-    sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
-                  board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
-    stride = sp.engine.record_stride
+    pipelined = mode == _lib.NET_TC and a.pipeline and N % 2 == 0
+    part = None
+    if pipelined:
+        from alphafive_b200.pipeline import SmPartition
+        from alphafive_b200.selfplay import PipelinedBatchedPlayer, PipelinedSelfPlay
+        try:
+            part = SmPartition.get(a.small_sms)
+        except Exception as e:                                # driver without green contexts: single stream
+            print(f"[bench] SM partition unavailable ({e}); single-stream schedule", file=sys.stderr)
+            pipelined = False
+    weights = glorot_init(S, 0)
+    if pipelined:
+        sp = PipelinedSelfPlay(None, n_games=N, weights=weights, training=True, seed=0, game_id_base=rank * N,
+                               small_sms=a.small_sms, board_size=S, simulation_per_step=sims,
+                               upper_simulation_per_step=upper)
+        net, eng0, Nk = sp.nets[0], sp.halves[0].engine, N // 2           # per-kernel timing: one half
+    else:
+        net = DeviceNet(S, N, weights, mode=mode)
+        sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
+                      board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
+        eng0, Nk = sp.engine, N
+    stride = eng0.record_stride
     rec_cap = N * 4                                          # records exchanged per step (plies finishing per step ~ N)
     gather_out = torch.empty((world, rec_cap, stride), dtype=torch.uint8, device="cuda") if world > 1 else None
     gather_cnt = torch.zeros(world, dtype=torch.int64, device="cuda")
@@ -235,20 +260,49 @@ def run_ours(a):
     c1 = sp.counters()
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel-class timing inside the same workload, CUDA events on the launch stream
-    prob, val = sp.prob, sp.value
-    tn0, tn1, tt0, tt1 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    # per-kernel-class timing inside the same workload, CUDA events on the launch stream(s).  Pipelined: one
+    # half batch, block convs on the big partition, everything else on the small one -- as in the timed run.
     reps = 20
+    if pipelined:
+        sp.pipe.drain()
     torch.cuda.synchronize()
-    nn_ms = tree_ms = 0.0
-    for _ in range(reps):
-        tn0.record(); net.forward_raw(sp.engine.planes_ptr, N, prob, val); tn1.record()
-        tt0.record(); sp.engine.step(prob, val); tt1.record()
+    if pipelined:
+        prob, val = sp.pipe.prob[0], sp.pipe.value[0]
+        fwd = lambda parts: check(lib.a5_net_forward_parts(net.handle, ct.c_void_p(eng0.planes_ptr), Nk, ptr(prob), ptr(val),
+                                                           parts, stream_ptr()))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        body_ms = small_ms = tree_ms = 0.0
+        for _ in range(reps):
+            with torch.cuda.stream(part.small):
+                ev[0].record(); fwd(1); ev[1].record()
+            part.big.wait_stream(part.small)
+            with torch.cuda.stream(part.big):
+                ev[2].record(); fwd(2); ev[3].record()
+            part.small.wait_stream(part.big)
+            with torch.cuda.stream(part.small):
+                fwd(4); ev[4].record(); eng0.step(prob, val); ev[5].record()
+            torch.cuda.synchronize()
+            body_ms += ev[2].elapsed_time(ev[3])
+            small_ms += ev[0].elapsed_time(ev[1]) + ev[3].elapsed_time(ev[4])
+            tree_ms += ev[4].elapsed_time(ev[5])
+        body_ms /= reps; small_ms /= reps; tree_ms /= reps
+        nn_ms = body_ms + small_ms
+        c2 = sp.counters()
+        with torch.cuda.stream(part.big):
+            lt = layer_times(net, eng0.planes_ptr, Nk, prob, val)
         torch.cuda.synchronize()
-        nn_ms += tn0.elapsed_time(tn1); tree_ms += tt0.elapsed_time(tt1)
-    nn_ms /= reps; tree_ms /= reps
-    c2 = sp.counters()
-    lt = layer_times(net, sp.engine.planes_ptr, N, prob, val) if mode == _lib.NET_TC else None
+    else:
+        prob, val = sp.prob, sp.value
+        tn0, tn1, tt0, tt1 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        nn_ms = tree_ms = 0.0
+        for _ in range(reps):
+            tn0.record(); net.forward_raw(eng0.planes_ptr, N, prob, val); tn1.record()
+            tt0.record(); eng0.step(prob, val); tt1.record()
+            torch.cuda.synchronize()
+            nn_ms += tn0.elapsed_time(tn1); tree_ms += tt0.elapsed_time(tt1)
+        nn_ms /= reps; tree_ms /= reps
+        c2 = sp.counters()
+        lt = layer_times(net, eng0.planes_ptr, N, prob, val) if mode == _lib.NET_TC else None
 
     t = torch.tensor([ms, float(c1["moves"] - c0["moves"]), float(c1["leaf_evals"] - c0["leaf_evals"]),
                       float(c1["sims"] - c0["sims"]), float(c1["games"] - c0["games"])], dtype=torch.float64, device="cuda")
@@ -264,8 +318,13 @@ def run_ours(a):
     import numpy as np
     del sp
     torch.cuda.empty_cache()
-    bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
-                       board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
+    if pipelined:
+        bp = PipelinedBatchedPlayer(None, n_players=N, weights=weights, training=True, seed=1, game_id_base=rank * N,
+                                    small_sms=a.small_sms, board_size=S, simulation_per_step=sims,
+                                    upper_simulation_per_step=upper)
+    else:
+        bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
+                           board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
     boards = np.zeros((N, S, S), np.int8); last = np.full(N, -1, np.int32)
     clear = np.ones(N, np.uint8)
     e2e_moves, e2e_t = 0, 0.0
@@ -292,7 +351,7 @@ def run_ours(a):
     if rank == 0:
         pk = peaks()
         flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * S * S / 121)
-        nn_tflops = flop * N / (nn_ms / 1000) / 1e12
+        nn_tflops = flop * Nk / (nn_ms / 1000) / 1e12
         dsel = max(1, c2["sims"] - c1["sims"])
         # SURVEY 8(d) algorithmic bytes per simulation with the measured d, A, f_leaf of this run
         C = S * S
@@ -309,12 +368,16 @@ def run_ours(a):
             "config": {"workload": workload_name(a, world), "board": S, "sims": sims, "upper_sims": upper,
                        "games_per_gpu": N, "net_mode": "fp32" if mode == _lib.NET_FP32 else "tc",
                        "l2": "per-pass working set (activations + node arenas) exceeds the 126 MB L2",
-                       "cuda_graph": not a.no_graph, "step": f"{sims} lock-step passes",
+                       "cuda_graph": (not a.no_graph) and not pipelined, "step": f"{sims} lock-step passes",
+                       "schedule": (f"two half batches of {Nk} games pipelined on SM-partitioned streams (CUDA green contexts: "
+                                    f"{part.n_big} SMs block convs, {part.n_small} SMs heads / tree pass / conv1)") if pipelined
+                                   else "single stream, CUDA-graph replay of one pass",
                        "preroll": f"{a.preroll_moves} untimed moves at {a.preroll_sims} sims to spread games over all plies"},
             "e2e": {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": bp.h2d_bytes,
-                    "d2h_bytes_per_step": bp.d2h_bytes, "api": "BatchedPlayer.get_actions(host boards) + device step/terminal"},
-            "gpu_launches": int((c1["passes"] - c0["passes"]) * (launches_per_pass(mode) + 1)),
-            "roofline": roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk),
+                    "d2h_bytes_per_step": bp.d2h_bytes, "api": ("PipelinedBatchedPlayer" if pipelined else "BatchedPlayer") + ".get_actions(host boards) + device step/terminal"},
+            "gpu_launches": int((c1["passes"] - c0["passes"]) * (launches_per_pass(mode) + 1) * (2 if pipelined else 1)),
+            "roofline": roofline_entry(mode, lt, nn_ms, nn_tflops, flop, Nk, C, pk,
+                                       part=(part.n_big, part.n_small) if pipelined else None),
             "roofline_tree": {"bound": "hbm", "kernel": "k_step (tree pass)", "achieved": tree_gbs, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": tree_gbs / pk["hbm"], "ms_per_launch": tree_ms,
                               "bytes_per_sim": bytes_per_sim, "d_bar": dbar, "a_bar": abar, "f_leaf": fleaf},
@@ -334,7 +397,7 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
+def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk, part=None):
     """Dominant kernel = k_tc_conv2 (nine launches per pass -- block3-conv1 and block4-conv1 run as one
     layer -- 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass / summed
     CUDA-event time of those launches."""
@@ -348,11 +411,17 @@ def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk):
     conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
     ach = conv_flop / (conv_ms / 1000) / 1e12
     tr = measured_traffic()
+    out_part = {}
+    if part:
+        out_part = {"boards_per_launch": N, "sms": part[0],
+                    "note": f"launch group of one half batch ({N} boards) on the {part[0]}-SM partition while the other "
+                            f"{part[1]} SMs run heads / tree pass / conv1 of the other half; peak is the whole chip's"}
+    traffic = tr.get("conv_dram_bytes_per_pass") * N / 4096.0 if tr else None
     return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 9 launches per pass)",
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
             "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
-            "traffic": tr.get("conv_dram_bytes_per_pass") if tr else None,
-            "traffic_note": tr.get("note") if tr else "no ncu capture committed for this build",
+            "traffic": traffic, **out_part,
+            "traffic_note": (tr.get("note") + f"; scaled to {N} boards") if tr else "no ncu capture committed for this build",
             "algorithmic_flop_per_pass": conv_flop, "issued_flop_factor": 3,
             "ms_per_pass": conv_ms, "ms_conv1": lt[0], "ms_heads": lt[11], "ms_layers": lt[1:11],
             "whole_net": whole}
