@@ -678,7 +678,13 @@ constexpr int C1M_KCH = 16;                                   // K = 128 as 16 c
 constexpr int C1M_ATILE = C1M_KCH * 128 * 16;                 // 32 KB
 constexpr int C1M_WBYTES = C1M_KCH * 64 * 16;                 // 16 KB
 constexpr int C1M_BW = 24;                                    // words per board: 8 per input plane
-constexpr int C1M_SMEM = 2 * C1M_ATILE + C1M_WBYTES + 32 * 16 + 128 + 128;
+#ifndef C1M_NA
+#define C1M_NA 2                                              // A tile buffers per CTA
+#endif
+#ifndef C1M_CTAS
+#define C1M_CTAS 2                                            // resident CTAs per SM the grid is sized for
+#endif
+constexpr int C1M_SMEM = C1M_NA * C1M_ATILE + C1M_WBYTES + 32 * 16 + 128 + 128;
 
 struct __align__(8) C1MBarriers {
   uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
                                                           int n, int ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* a_buf = smem;                                       // 2 A tiles [kchunk 10][row 128][8]
-  uint8_t* w_buf = smem + 2 * C1M_ATILE;                       // [kchunk 10][hi 32 | lo 32][8]
+  uint8_t* w_buf = smem + C1M_NA * C1M_ATILE;                  // [kchunk 16][hi 32 | lo 32][8]
   uint4* s_lut = (uint4*)(w_buf + C1M_WBYTES);                 // window pattern -> 8 halves (5 used)
   float* s_bias = (float*)(s_lut + 32);
   C1MBarriers* B = (C1MBarriers*)(s_bias + 32);
@@ -723,7 +729,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
     s_lut[tid] = make_uint4(((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u),
                             ((b & 4u) ? 0x3C00u : 0u) | ((b & 8u) ? 0x3C000000u : 0u), (b & 16u) ? 0x3C00u : 0u, 0u);
   }
-  for (int i = tid; i < 2 * 128; i += C1M_THREADS)             // the 16th K chunk of both tiles stays zero
+  for (int i = tid; i < C1M_NA * 128; i += C1M_THREADS)        // the 16th K chunk of every tile buffer stays zero
     *(uint4*)(a_buf + (i >> 7) * C1M_ATILE + (15 * 128 + (i & 127)) * 16) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 32) s_bias[tid] = bias[tid];
   if (tid == 0) {
@@ -794,7 +800,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B->a_full[ab]);
-      if (++ab == 2) { ab = 0; aph ^= 1; }
+      if (++ab == C1M_NA) { ab = 0; aph ^= 1; }
       cur = nxt;
     }
   } else if (warp == C1M_BUILD_WARPS) {
@@ -816,7 +822,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
         tc_commit(&B->t_full[tb]);
       }
       __syncwarp();
-      if (++ab == 2) { ab = 0; aph ^= 1; }
+      if (++ab == C1M_NA) { ab = 0; aph ^= 1; }
       if (++tb == 2) { tb = 0; tph ^= 1; }
     }
   } else {
@@ -1048,7 +1054,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   const long long nrows1 = (long long)n * ps.per_board;
   if (parts & A5_NET_PART_FRONT) {
     const int ntiles = (int)((nrows1 + 127) / 128);
-    const int grid1 = ntiles < 2 * tc->front_sms ? ntiles : 2 * tc->front_sms;
+    const int grid1 = ntiles < C1M_CTAS * tc->front_sms ? ntiles : C1M_CTAS * tc->front_sms;
     k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits);
     A5_CUDA(cudaGetLastError());
     k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
