@@ -40,6 +40,8 @@ struct TCfg {
 
 struct TCLayer {
   const __half* src; int src_ch;
+  const __half* src2; int src2_ch;  // optional second 3x3 segment (two convs of different inputs merged into one layer)
+  int n0;                          // output columns of the first segment (== cout without src2); src2 fills [n0, cout)
   const __half* res; int res_ch;
   const __half* wpk;
   const float* bias;
@@ -372,15 +374,49 @@ __device__ __forceinline__ void tc_mma2s(uint32_t d_tmem, uint32_t a_lo, uint32_
 // nine-tap main slabs (m0 r0 r1 m1 r2 r3 for 2 + 4), so that every window of (slab buffers - 1)
 // consecutive slabs holds a main slab's worth of MMA time for the prefetch of the slab after it.
 struct SlabSeq {
-  int M, R, mi, ri;
-  __device__ __forceinline__ SlabSeq(int m, int r) : M(m), R(r), mi(0), ri(0) {}
+  int M, R, lead, mi, ri;
+  // lead: main slabs that must come before the first residual slab -- every output column has to be
+  // initialised by the first stage of the 3x3 segment that owns it before a residual MMA accumulates into it
+  __device__ __forceinline__ SlabSeq(int m, int r, int lead_ = 1) : M(m), R(r), lead(lead_), mi(0), ri(0) {}
   // returns true for a residual slab; idx = its index within its kind
   __device__ __forceinline__ bool next(int& idx) {
-    const bool res = mi == M || ri < (mi * R) / M;
+    const bool res = mi == M || (mi >= lead && ri < ((mi - lead + 1) * R) / (M - lead + 1));
     idx = res ? ri++ : mi++;
     return res;
   }
 };
+
+// What one K slab of a layer is: where its activations come from, how many taps it carries, which output
+// columns its MMAs produce (a layer may merge two 3x3 convs of different inputs: columns [0, n0) and
+// [n0, cout); the 1x1 residual slabs always cover all cout columns), and where its weight stages start --
+// `wstage` in units of this segment's per-CTA stage size, `wbase` in bytes of per-CTA weights before it.
+struct SlabInfo {
+  const __half* X; int xch, kc0, ntap, n, col0;
+  uint32_t sbytes, wbase; int wstage;
+};
+__device__ __forceinline__ uint32_t seg_stage_bytes(const TCLayer& L, int n) {
+  return L.fold ? 4u * (uint32_t)(n + n / 2) * 16u : 4u * (uint32_t)n * 16u;   // [kchunk 4][X rows | S rows][8] halves
+}
+__device__ __forceinline__ SlabInfo slab_info(const TCLayer& L, bool is_res, int idx) {
+  SlabInfo s;
+  const int m0 = L.src_ch / TC_KS, m1 = L.src2 ? L.src2_ch / TC_KS : 0;
+  const int n1 = L.cout - L.n0;
+  const uint32_t sb0 = seg_stage_bytes(L, L.n0), sb1 = L.src2 ? seg_stage_bytes(L, n1) : 0u;
+  if (is_res) {
+    s.X = L.res; s.xch = L.res_ch; s.kc0 = idx * (TC_KS / 8); s.ntap = 1; s.n = L.cout; s.col0 = 0;
+    s.sbytes = seg_stage_bytes(L, L.cout);
+    s.wbase = sb0 * (uint32_t)(m0 * L.ntaps) + sb1 * (uint32_t)(m1 * L.ntaps);
+    s.wstage = idx;
+  } else if (idx < m0) {
+    s.X = L.src; s.xch = L.src_ch; s.kc0 = idx * (TC_KS / 8); s.ntap = L.ntaps; s.n = L.n0; s.col0 = 0;
+    s.sbytes = sb0; s.wbase = 0; s.wstage = idx * L.ntaps;
+  } else {
+    const int j = idx - m0;
+    s.X = L.src2; s.xch = L.src2_ch; s.kc0 = j * (TC_KS / 8); s.ntap = L.ntaps; s.n = n1; s.col0 = L.n0;
+    s.sbytes = sb1; s.wbase = sb0 * (uint32_t)(m0 * L.ntaps); s.wstage = j * L.ntaps;
+  }
+  return s;
+}
 
 template <int T, bool RESW, int HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc_conv2(const __grid_constant__ TCLayer L) {
@@ -399,11 +435,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   const bool fold = L.fold != 0;
   const int cpt = fold ? 2 * cout : cout;                  // TMEM columns per M tile
   const int nbuf = (T * cpt <= 256) ? 2 : 1;
-  const int main_slabs = L.src_ch / TC_KS, res_slabs = L.res ? L.res_ch / TC_KS : 0;
+  const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
   const int nslabs = main_slabs + res_slabs;
-  const int nstage = main_slabs * L.ntaps + res_slabs;
-  const int xr = fold ? cout : cout / 2, sr = cout / 2;    // rows of the two parts of this CTA's stage
-  const uint32_t stage_bytes = 4u * (uint32_t)(xr + sr) * 16u;
+  const int lead = L.src2 ? L.src_ch / TC_KS + 1 : 1;      // see SlabSeq
   // pair-groups: the pair handles groups 2 pg (leader) and 2 pg + 1 (peer); both CTAs run the
   // same number of iterations (rows past nrows are padding and masked in the epilogue)
   const int npairs = (L.ngroups + 1) / 2;
@@ -438,13 +472,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     pdl_wait();                                              // the layer(s) that wrote src / res are complete
     for (int g = g_first; g < g_end; g += g_step) {
       const long long r0 = L.row0 + (long long)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS - HALO;
-      SlabSeq seq(main_slabs, res_slabs);
+      SlabSeq seq(main_slabs, res_slabs, lead);
       for (int s = 0; s < nslabs; ++s) {
         int sidx;
         const bool is_res = seq.next(sidx);
-        const __half* X = is_res ? L.res : L.src;
-        const int xch = is_res ? L.res_ch : L.src_ch;
-        const int kc0 = sidx * (TC_KS / 8);
+        const SlabInfo si = slab_info(L, is_res, sidx);
+        const __half* X = si.X;
+        const int xch = si.xch, kc0 = si.kc0;
         mbar_wait(&B->a_empty[ab], aph ^ 1);
         if (lane == 0) dbg_mark(L.dbg, 0, dn);
         if (elect_one()) {
@@ -464,32 +498,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     }
   } else if (warp == TC_W_WARP) {
     // ===================== W producer (each CTA loads its half of every weight stage) =====================
-    const __half* wsrc0 = L.wpk + (size_t)rank * (stage_bytes / 2);
+    // packed weights: per segment, per stage, the shares of the two CTAs back to back
+    const uint8_t* wsrc0 = (const uint8_t*)L.wpk;
     if (RESW) {
       if (elect_one()) {
-        mbar_expect_tx(&B->w_full[0], (uint32_t)nstage * stage_bytes);
-        for (int t = 0; t < nstage; ++t)
-          bulk_g2s(w_buf + (size_t)t * stage_bytes, wsrc0 + (size_t)t * stage_bytes, stage_bytes, &B->w_full[0]);
+        uint32_t total = 0;
+        for (int kind = 0; kind < 2; ++kind)
+          for (int sidx = 0; sidx < (kind ? res_slabs : main_slabs); ++sidx) {
+            const SlabInfo si = slab_info(L, kind != 0, sidx);
+            total += si.sbytes * (uint32_t)si.ntap;
+          }
+        mbar_expect_tx(&B->w_full[0], total);
+        for (int kind = 0; kind < 2; ++kind)
+          for (int sidx = 0; sidx < (kind ? res_slabs : main_slabs); ++sidx) {
+            const SlabInfo si = slab_info(L, kind != 0, sidx);
+            for (int t = 0; t < si.ntap; ++t) {
+              const uint32_t off = si.wbase + (uint32_t)(si.wstage + t) * si.sbytes;      // per-CTA byte offset
+              bulk_g2s(w_buf + off, wsrc0 + 2u * (size_t)off + (size_t)rank * si.sbytes, si.sbytes, &B->w_full[0]);
+            }
+          }
       }
       __syncwarp();
     } else {
       int ws = 0, wph = 0;
       for (int g = g_first; g < g_end; g += g_step) {
-        SlabSeq seq(main_slabs, res_slabs);
+        SlabSeq seq(main_slabs, res_slabs, lead);
         for (int s = 0; s < nslabs; ++s) {
           int sidx;
           const bool is_res = seq.next(sidx);
-          const int ntap = is_res ? 1 : L.ntaps;
-          // stage (slab, tap) of the packed weights: main stages slab-major, then the residual stages
-          const __half* wsrc = wsrc0 + (size_t)(is_res ? main_slabs * L.ntaps + sidx : sidx * L.ntaps) * stage_bytes;
-          for (int t = 0; t < ntap; ++t) {
+          const SlabInfo si = slab_info(L, is_res, sidx);
+          for (int t = 0; t < si.ntap; ++t) {
+            const uint32_t off = si.wbase + (uint32_t)(si.wstage + t) * si.sbytes;
             mbar_wait(&B->w_empty[ws], wph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&B->w_full[ws], stage_bytes);
-              bulk_g2s(w_buf + ws * TC2_WSTAGE_MAX, wsrc, stage_bytes, &B->w_full[ws]);
+              mbar_expect_tx(&B->w_full[ws], si.sbytes);
+              bulk_g2s(w_buf + ws * TC2_WSTAGE_MAX, wsrc0 + 2u * (size_t)off + (size_t)rank * si.sbytes, si.sbytes, &B->w_full[ws]);
             }
             __syncwarp();
-            wsrc += stage_bytes;                           // 2 CTAs x stage_bytes, in halfs
             if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
           }
         }
@@ -504,7 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
       __syncwarp();
     }
     for (int g = g_first; g < g_end; g += g_step) {
-      SlabSeq seq(main_slabs, res_slabs);
+      SlabSeq seq(main_slabs, res_slabs, lead);
       for (int s = 0; s < nslabs; ++s) {
         int sidx;
         const int ntap = seq.next(sidx) ? 1 : L.ntaps;
@@ -526,19 +571,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
     // ===================== MMA issuers (leader): M = 256 over both CTAs, T/2 tiles each =====================
     const int m0 = (warp == 1) ? 0 : T / 2;
     unsigned long long* dbg = (warp == 1) ? L.dbg : nullptr;
-    const uint32_t idesc = instr_desc(256, cout), idesc2 = instr_desc(256, 2 * cout);
-    const uint32_t w_lbo = (uint32_t)(xr + sr) * 16u;
     // descriptor low-word deltas (the start-address field counts 16-byte units)
     constexpr uint32_t A_TILE = 128u * 16u / 16u;
     constexpr uint32_t A_K16 = 2u * Cfg::PLANE / 16u;
     constexpr uint32_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;
-    const uint32_t w_k16 = 2u * w_lbo / 16u;
-    const uint32_t w_s16 = (uint32_t)xr;                    // X -> S part of a stage (16-byte units)
     const uint64_t ad64 = smem_desc(smem_u32(a_buf) + (uint32_t)HALO * 16u, Cfg::PLANE, 128);
-    const uint64_t bd64 = smem_desc(smem_u32(w_buf), w_lbo, 128);
-    const uint32_t a_hi = (uint32_t)(ad64 >> 32), b_hi = (uint32_t)(bd64 >> 32);
-    const uint32_t ad_base = (uint32_t)ad64 + (uint32_t)m0 * A_TILE, bd_base = (uint32_t)bd64;
-    const uint32_t w_step = RESW ? stage_bytes / 16u : (uint32_t)(TC2_WSTAGE_MAX / 16);
+    const uint32_t a_hi = (uint32_t)(ad64 >> 32), b_hi = (uint32_t)(smem_desc(0, 0, 128) >> 32);
+    const uint32_t ad_base = (uint32_t)ad64 + (uint32_t)m0 * A_TILE;
+    const uint32_t w_addr16 = (smem_u32(w_buf) & 0x3FFFFu) >> 4;
     int sh[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
@@ -550,13 +590,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
       tc_fence_after();
       if (lane == 0) dbg_mark(dbg, 1, dn);
       const uint32_t d0 = tmem + (uint32_t)(tb * T * cpt + m0 * cpt);
-      SlabSeq seq(main_slabs, res_slabs);
+      SlabSeq seq(main_slabs, res_slabs, lead);
       for (int s = 0; s < nslabs; ++s) {
         int sidx;
         const bool is_res = seq.next(sidx);
-        const int ntap = is_res ? 1 : L.ntaps;
-        // RESW: first resident stage of this slab
-        uint32_t bd = bd_base + (uint32_t)(is_res ? main_slabs * L.ntaps + sidx : sidx * L.ntaps) * w_step;
+        const SlabInfo si = slab_info(L, is_res, sidx);
+        const int ntap = si.ntap;
+        // this slab's B operand: stage layout [kchunk 4][X rows | S rows][8]; fold: X = n rows (w_hi in the
+        // leader, w_lo in the peer), S = n/2 rows of w_hi; else X = n/2 rows of w_hi, S = n/2 rows of w_lo
+        const uint32_t rows = fold ? (uint32_t)(si.n + si.n / 2) : (uint32_t)si.n;
+        const uint32_t w_k16 = 2u * rows, w_s16 = fold ? (uint32_t)si.n : (uint32_t)(si.n / 2);
+        const uint32_t idesc = instr_desc(256, si.n), idesc2 = instr_desc(256, 2 * si.n);
+        const uint32_t w_step = RESW ? si.sbytes / 16u : (uint32_t)(TC2_WSTAGE_MAX / 16);
+        const uint32_t bd_lbo = rows << 16;                  // K-adjacent core matrices are rows * 16 bytes apart
+        uint32_t bd = (w_addr16 + (si.wbase + (uint32_t)si.wstage * si.sbytes) / 16u) | bd_lbo;   // RESW: first resident stage
+        const uint32_t dcol = d0 + (uint32_t)si.col0;
         mbar_wait_cluster(&B->a_full[ab], aph);
         tc_fence_after();
         if (lane == 0) dbg_mark(dbg, 1, dn);
@@ -569,8 +617,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
               tc_fence_after();
             }
             const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
-            const uint32_t bd0 = RESW ? bd : bd_base + (uint32_t)ws * w_step;
-            const uint32_t first = (uint32_t)(s | t);
+            const uint32_t bd0 = RESW ? bd : ((w_addr16 + (uint32_t)ws * w_step) | bd_lbo);
+            // the first stage of a 3x3 segment initialises the columns that segment owns
+            const uint32_t first = (uint32_t)(si.wstage | t) | (is_res ? 1u : 0u);
             const bool last_tap = t == ntap - 1;
             if (elect_one()) {
               if (fold) {
@@ -578,10 +627,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
                 for (int m = 0; m < T / 2; ++m) {
 #pragma unroll
                   for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, a_hi, bd0 + k * w_k16, b_hi, idesc2, (first | k) != 0);
+                    tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, a_hi, bd0 + k * w_k16, b_hi, idesc2, (first | k) != 0);
 #pragma unroll
                   for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, a_hi, bd0 + k * w_k16 + w_s16, b_hi, idesc, 1u);
+                    tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, a_hi, bd0 + k * w_k16 + w_s16, b_hi, idesc, 1u);
                 }
               } else {
 #pragma unroll
@@ -590,7 +639,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
                   for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
 #pragma unroll
                     for (int k = 0; k < TC_KS / 16; ++k)
-                      tc_mma2s(d0 + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
+                      tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
                                bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), b_hi, idesc, (first | pass | k) != 0);
                   }
                 }
@@ -1086,6 +1135,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     }
     if (merged) { L.bias = tc->bias_m; L.out2 = tc->act[B4H]; L.split = 32; }
     L.cout = D.cout; L.ntaps = 9;
+    L.n0 = D.cout;
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
