@@ -123,8 +123,9 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
     tc_fence_after();
     dbg_mark(edbg, 2, dn);                               // accumulators ready
     if (L.head_ch) {
-      // head layers (cout = 32): a warp takes whole rows of one M tile, so the 1x1 head conv
-      // sees all 32 channels of its position.
+      // head layers: columns [0, 32) of every tile feed the fused 1x1 head conv -- a warp takes whole rows
+      // of one M tile, so the head conv sees all 32 channels of its position (cout > 32: the remaining
+      // columns are plain units, below)
       // the four warps of a lane quadrant share the T tiles; with T = 2 two warps split the 16 policy-head
       // outputs of a tile between them (each recomputes the 32 activations it needs)
       constexpr int NPART = (TC_EPI_WARPS / 4) / T > 0 ? (TC_EPI_WARPS / 4) / T : 1;
@@ -232,8 +233,10 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
     int cur_m = -1;
     bool real = false;
     uint32_t q = 0;
-    for (int u = sub; !L.head_ch && u < T * nc; u += TC_EPI_WARPS / 4) {
-      const int m = u / nc, c0 = (u - m * nc) << 4;
+    const int hcols = L.head_ch ? 32 : 0;                    // columns consumed by the head path above
+    const int ncp = (cout - hcols) >> 4;                     // plain 16-column units per tile
+    for (int u = sub; u < T * ncp; u += TC_EPI_WARPS / 4) {
+      const int m = u / ncp, c0 = hcols + ((u - m * ncp) << 4);
       if (m != cur_m) {
         cur_m = m;
         q = (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
@@ -266,7 +269,7 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
           f[4 * e + j] = x > 0.0f ? x : neg;
         }
       }
-      if (L.out) {
+      if (L.out || L.out2) {
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc) {
           uint32_t hi[4], lo[4];
@@ -374,13 +377,14 @@ __device__ __forceinline__ void tc_mma2s(uint32_t d_tmem, uint32_t a_lo, uint32_
 // nine-tap main slabs (m0 r0 r1 m1 r2 r3 for 2 + 4), so that every window of (slab buffers - 1)
 // consecutive slabs holds a main slab's worth of MMA time for the prefetch of the slab after it.
 struct SlabSeq {
-  int M, R, lead, mi, ri;
-  // lead: main slabs that must come before the first residual slab -- every output column has to be
-  // initialised by the first stage of the 3x3 segment that owns it before a residual MMA accumulates into it
-  __device__ __forceinline__ SlabSeq(int m, int r, int lead_ = 1) : M(m), R(r), lead(lead_), mi(0), ri(0) {}
+  int M, R, rfirst, mi, ri;
+  // rfirst (layers with two 3x3 segments): the group starts with a residual slab, whose first MMA initialises
+  // ALL output columns (the segments then only accumulate), and the rest alternate r0 m0 r1 m1 r2 m2 r3 --
+  // otherwise a residual MMA could hit columns whose segment has not started yet
+  __device__ __forceinline__ SlabSeq(int m, int r, int rfirst_ = 0) : M(m), R(r), rfirst(rfirst_), mi(0), ri(0) {}
   // returns true for a residual slab; idx = its index within its kind
   __device__ __forceinline__ bool next(int& idx) {
-    const bool res = mi == M || (mi >= lead && ri < ((mi - lead + 1) * R) / (M - lead + 1));
+    const bool res = mi == M || (rfirst ? ri < 1 + (mi * (R - 1)) / M : ri < (mi * R) / M);
     idx = res ? ri++ : mi++;
     return res;
   }
@@ -437,7 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   const int nbuf = (T * cpt <= 256) ? 2 : 1;
   const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
   const int nslabs = main_slabs + res_slabs;
-  const int lead = L.src2 ? L.src_ch / TC_KS + 1 : 1;      // see SlabSeq
+  const int lead = L.src2 ? 1 : 0;                         // SlabSeq::rfirst
   // pair-groups: the pair handles groups 2 pg (leader) and 2 pg + 1 (peer); both CTAs run the
   // same number of iterations (rows past nrows are padding and masked in the epilogue)
   const int npairs = (L.ngroups + 1) / 2;
@@ -618,8 +622,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
             }
             const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
             const uint32_t bd0 = RESW ? bd : ((w_addr16 + (uint32_t)ws * w_step) | bd_lbo);
-            // the first stage of a 3x3 segment initialises the columns that segment owns
-            const uint32_t first = (uint32_t)(si.wstage | t) | (is_res ? 1u : 0u);
+            // the group's first MMA initialises the accumulator columns: the first stage of the (single) 3x3
+            // segment, or -- two segments -- the first residual slab, which spans all columns
+            const uint32_t first = lead ? (is_res ? (uint32_t)sidx : 1u) : ((uint32_t)(si.wstage | t) | (is_res ? 1u : 0u));
             const bool last_tap = t == ntap - 1;
             if (elect_one()) {
               if (fold) {
@@ -668,6 +673,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// One 3x3 / 1x1 segment of a merged layer, non-fold layout: per stage (32-channel slab, tap) the shares of the two
+// CTAs, each [kchunk 4][X: n/2 rows of w_hi | S: n/2 rows of w_lo][8].  `wb` (optional) continues `w` along N.
+__global__ void k_tc_pack2_seg(const float* __restrict__ w, const float* __restrict__ wb, int na, int ntaps, int cin, int n,
+                               __half* __restrict__ out) {
+  const int nstages = (cin / TC_KS) * ntaps;
+  const long long per_cta = (long long)4 * n * 8;          // halfs
+  const long long total = (long long)nstages * 2 * per_cta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int stage = (int)(i / (2 * per_cta));
+    const int r = (int)(i % (2 * per_cta));
+    const int cta = r / (int)per_cta, r2 = r % (int)per_cta;
+    const int j = r2 / (n * 8), row = (r2 / 8) % n, e = r2 % 8;
+    const int half_n = n / 2;
+    const int lo = row >= half_n;
+    const int col = cta * half_n + (lo ? row - half_n : row);
+    const int slab = stage / ntaps, tap = stage % ntaps;
+    const size_t kk = (size_t)tap * cin + slab * TC_KS + j * 8 + e;
+    float x = !wb ? w[kk * n + col] : (col < na ? w[kk * na + col] : wb[kk * (n - na) + (col - na)]);
+    x *= W_SCALE;
+    const __half h = __float2half_rn(x);
+    out[i] = lo ? __float2half_rn(x - __half2float(h)) : h;
   }
 }
 
@@ -980,6 +1009,12 @@ struct a5_tc_state {
   // ~44-cycle MMA floor, and the 128-channel input is read once)
   __half* wpk2_m = nullptr;
   float* bias_m = nullptr;
+  // block3-conv2 (32->32 + r128) and block4-conv2 (64->64 + r128) both add a 1x1 projection of block2's
+  // output (network.py:52-56,68,79): as ONE layer with two 3x3 segments (columns [0,32) and [32,96)) and a
+  // shared N = 96 residual segment the 302 MB tensor is read once instead of twice
+  __half* wpk2_m2 = nullptr;
+  float* bias_m2 = nullptr;
+  int merge2 = 1;               // A5_TC_MERGE2=0: run the two layers separately
   __half* wpk_c1 = nullptr;     // conv1 weights for k_tc_conv1m
   uint32_t* c1_bits = nullptr;  // bitboards of the input planes (k_c1_bits)
   int zigzag = 1;               // A5_TC_ZIGZAG=0: every layer walks the groups in ascending order
@@ -1034,6 +1069,8 @@ int tc_alloc(a5_net* net) {
   }
   A5_CUDA(cudaMalloc(&tc->wpk2_m, (size_t)(128 / TC_KS) * 9 * 2 * 4 * 96 * 8 * sizeof(__half)));
   A5_CUDA(cudaMalloc(&tc->bias_m, 96 * sizeof(float)));
+  A5_CUDA(cudaMalloc(&tc->wpk2_m2, (size_t)2 * (9 * 2048 + 18 * 4096 + 4 * 6144)));
+  A5_CUDA(cudaMalloc(&tc->bias_m2, 96 * sizeof(float)));
   A5_CUDA(cudaMalloc(&tc->wpk_c1, C1M_WBYTES));
   A5_CUDA(cudaMalloc(&tc->c1_bits, (size_t)net->max_batch * C1M_BW * sizeof(uint32_t)));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv1m, cudaFuncAttributeMaxDynamicSharedMemorySize, C1M_SMEM));
@@ -1047,6 +1084,7 @@ int tc_alloc(a5_net* net) {
   tc->zigzag = ((ev = getenv("A5_TC_ZIGZAG")) && atoi(ev) == 0) ? 0 : 1;
   tc->resw = ((ev = getenv("A5_TC_RESW")) && atoi(ev) == 0) ? 0 : 1;
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
+  tc->merge2 = ((ev = getenv("A5_TC_MERGE2")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
@@ -1063,6 +1101,8 @@ void tc_free(a5_net* net) {
   for (int i = 0; i < 11; ++i) cudaFree(net->tc->wpk2[i]);
   cudaFree(net->tc->wpk2_m);
   cudaFree(net->tc->bias_m);
+  cudaFree(net->tc->wpk2_m2);
+  cudaFree(net->tc->bias_m2);
   cudaFree(net->tc->wpk_c1);
   cudaFree(net->tc->c1_bits);
   heads_free(net->tc->heads);
@@ -1086,6 +1126,16 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
   A5_CUDA(cudaGetLastError());
   A5_CUDA(cudaMemcpyAsync(tc->bias_m, net->bias[5], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A5_CUDA(cudaMemcpyAsync(tc->bias_m + 32, net->bias[7], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  {
+    // merged conv2 layer: [block3-conv2 3x3 | block4-conv2 3x3 | (block3-res | block4-res) 1x1]
+    uint8_t* base = (uint8_t*)tc->wpk2_m2;
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_C2_K], nullptr, 0, 9, 32, 32, (__half*)base);
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B4_C2_K], nullptr, 0, 9, 64, 64, (__half*)(base + 2 * 9 * 2048));
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_RES_K], t[T_B4_RES_K], 32, 1, 128, 96, (__half*)(base + 2 * (9 * 2048 + 18 * 4096)));
+    A5_CUDA(cudaGetLastError());
+    A5_CUDA(cudaMemcpyAsync(tc->bias_m2, net->bias[6], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    A5_CUDA(cudaMemcpyAsync(tc->bias_m2 + 32, net->bias[8], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return heads_set_weights(net, tc->heads, t, st);
 }
 
@@ -1112,13 +1162,15 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
+  int nexec = 0;                                   // conv layers launched so far (alternating walk direction)
   for (int l = 1; l <= 10 && (parts & A5_NET_PART_BODY); ++l) {
     TcLayerDef D = kTcLayers[l];
     TCLayer L;
     memset(&L, 0, sizeof(L));
     const bool merged = tc->merge && l == 5;      // block3-conv1 + block4-conv1 as one cout = 96 layer
-    if (tc->merge && l == 7) { TC_MARK(1 + l); continue; }
-    if (merged) D.cout = 96;
+    const bool merged2 = tc->merge2 && l == 6;    // block3-conv2 + block4-conv2 (+ both residual projections)
+    if ((tc->merge && l == 7) || (tc->merge2 && l == 8)) { TC_MARK(1 + l); continue; }
+    if (merged || merged2) D.cout = 96;
     L.src = tc->act[D.src]; L.src_ch = D.cin;
     L.res = D.res_src >= 0 ? tc->act[D.res_src] : nullptr; L.res_ch = D.res_cin;
     L.bias = net->bias[l];
@@ -1136,12 +1188,16 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     if (merged) { L.bias = tc->bias_m; L.out2 = tc->act[B4H]; L.split = 32; }
     L.cout = D.cout; L.ntaps = 9;
     L.n0 = D.cout;
+    if (merged2) {
+      L.src2 = tc->act[B4H]; L.src2_ch = 64; L.n0 = 32;
+      L.bias = tc->bias_m2; L.out2 = tc->act[B4O]; L.split = 32;
+    }
     int k = 0;
     for (int ky = -1; ky <= 1; ++ky)
       for (int kx = -1; kx <= 1; ++kx) L.shifts[k++] = ky * ps.pitch + kx;
     L.fold = (D.cout <= 64) ? tc->fold : 0;
     // conv1 writes ascending; from there on every layer starts where its inputs were touched last
-    L.reverse = tc->zigzag && (l == 1 || l == 3 || l == 5 || l == 8 || l == 10);
+    L.reverse = tc->zigzag && (nexec++ % 2 == 0);
     L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
@@ -1151,7 +1207,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
       const int ngroups = (int)((nrows + T * 128 - 1) / (T * 128));
       const int npairs = (ngroups + 1) / 2;
       L.ngroups = ngroups;
-      L.wpk = merged ? tc->wpk2_m : tc->wpk2[l];
+      L.wpk = merged ? tc->wpk2_m : (merged2 ? tc->wpk2_m2 : tc->wpk2[l]);
       const int maxpairs = tc->num_sms / 2;
       const int grid = 2 * (npairs < maxpairs ? npairs : maxpairs);
       const bool h16 = ps.pitch + 1 <= 16;
@@ -1161,7 +1217,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
       const int nstage = (D.cin / TC_KS) * 9 + res_slabs;
       // weights resident in shared memory when the whole set fits beside enough slab buffers: two if
       // every slab carries nine taps of MMAs, three if one-tap residual slabs must be prefetched past
-      const int wres = (nstage * 4 * (xr + sr) * 16 + 127) & ~127;
+      const int wres = merged2 ? 9 * 2048 + 18 * 4096 + 4 * 6144 : (nstage * 4 * (xr + sr) * 16 + 127) & ~127;
       const int nsb_res = (TC2_SMEM_LIMIT - TC2_MISC - wres) / slab;
       const bool resw = tc->resw && nsb_res >= (res_slabs ? 3 : 2);
       L.w_bytes = resw ? wres : TC2_WSTAGES * TC2_WSTAGE_MAX;

@@ -29,9 +29,9 @@ val = torch.empty((n,), device="cuda")
 ms = (C.c_float * 12)()
 check(fn(net.handle, ptr(planes), n, 3, ptr(prob), ptr(val), ms, stream_ptr()))        # warm-up
 check(fn(net.handle, ptr(planes), n, reps, ptr(prob), ptr(val), ms, stream_ptr()))
-names = ["conv1", "b1c1 32>64", "b1c2 64>64+r32", "b2c1 64>128", "b2c2 128>128+r64", "b3c1+b4c1 128>96", "b3c2 32>32+r128",
-         "(merged into b3c1)", "b4c2 64>64+r128", "b5c1 64>32", "b5c2 32>32+r64", "heads"]
-kmac = [0, 288 * 64, 608 * 64, 576 * 128, 1216 * 128, 1152 * 96, 416 * 32, 0, 704 * 64, 576 * 32, 352 * 32, 0]
+names = ["conv1", "b1c1 32>64", "b1c2 64>64+r32", "b2c1 64>128", "b2c2 128>128+r64", "b3c1+b4c1 128>96", "b3c2+b4c2 +r128>96",
+         "(merged into b3c1)", "(merged into b3c2)", "b5c1 64>32", "b5c2 32>32+r64", "heads"]
+kmac = [0, 288 * 64, 608 * 64, 576 * 128, 1216 * 128, 1152 * 96, 416 * 32 + 704 * 64, 0, 0, 576 * 32, 352 * 32, 0]
 pos = n * (S + 1) ** 2
 tot = 0.0
 for i, nm in enumerate(names):

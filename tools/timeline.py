@@ -41,7 +41,7 @@ for layer in layers:
             if x > 0:
                 ev.append((int(x - t0), role, i))
     ev.sort()
-    nslab = {1: 1, 2: 3, 3: 2, 4: 6, 5: 4, 6: 5, 7: 4, 8: 6, 9: 2, 10: 3}[layer]
+    nslab = {1: 1, 2: 3, 3: 2, 4: 6, 5: 4, 6: 7, 7: 4, 8: 6, 9: 2, 10: 3}[layer]
     per_group_m = 3 + nslab
     for t, role, i in ev[: ngr * (per_group_m + 2 + nslab + 48 * nslab)]:
         if role == 1:
