@@ -398,10 +398,10 @@ def run_ours(a):
 
 
 def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk, part=None):
-    """Dominant kernel = k_tc_conv2 (nine launches per pass -- block3-conv1 and block4-conv1 run as one
-    layer -- 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass / summed
+    """Dominant kernel = k_tc_conv2 (eight launches per pass -- block3/block4 conv1 run as one layer, and so
+    do block3/block4 conv2 -- 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass / summed
     CUDA-event time of those launches."""
-    whole = {"kernel": "whole net forward (bitboards + conv1 + 9 block convs + heads = 12 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
+    whole = {"kernel": "whole net forward (bitboards + conv1 + 8 block-conv launches + heads = 11 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
              "ms_per_pass": nn_ms, "flop_per_leaf": flop}
     if lt is None:
         return {"bound": "tensor", "kernel": "policy/value net forward, fp32 CUDA-core path", "achieved": nn_tflops,
@@ -417,7 +417,7 @@ def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk, part=None):
                     "note": f"launch group of one half batch ({N} boards) on the {part[0]}-SM partition while the other "
                             f"{part[1]} SMs run heads / tree pass / conv1 of the other half; peak is the whole chip's"}
     traffic = tr.get("conv_dram_bytes_per_pass") * N / 4096.0 if tr else None
-    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 9 launches per pass)",
+    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)",
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
             "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
             "traffic": traffic, **out_part,
@@ -428,8 +428,8 @@ def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk, part=None):
 
 
 def launches_per_pass(mode):
-    # tensor-core path: bitboards + conv1 + 9 block convs + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
-    return 12 if mode == 1 else 15
+    # tensor-core path: bitboards + conv1 + 8 block-conv launches + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
+    return 11 if mode == 1 else 15
 
 
 CONV_MAC_PER_CELL = 485_376          # the ten 3x3(+1x1) block convs, MACs per board cell (58,730,496 @ 11x11)
