@@ -613,49 +613,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
         tc_fence_after();
         if (lane == 0) dbg_mark(dbg, 1, dn);
         const uint32_t ad_slab = ad_base + (uint32_t)(ab * (Cfg::SLAB / 16));
+        // one (slab, tap) stage: the MMAs of this issuer's tiles
+        auto issue_stage = [&](const uint32_t ad0, const uint32_t bd0, const uint32_t first) {
+          if (fold) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          if (t < ntap) {
-            if (!RESW) {
+            for (int m = 0; m < T / 2; ++m) {
+#pragma unroll
+              for (int k = 0; k < TC_KS / 16; ++k)
+                tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, a_hi, bd0 + k * w_k16, b_hi, idesc2, (first | k) != 0);
+#pragma unroll
+              for (int k = 0; k < TC_KS / 16; ++k)
+                tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, a_hi, bd0 + k * w_k16 + w_s16, b_hi, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < T / 2; ++m) {
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
+#pragma unroll
+                for (int k = 0; k < TC_KS / 16; ++k)
+                  tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
+                           bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), b_hi, idesc, (first | pass | k) != 0);
+              }
+            }
+          }
+        };
+        // the group's first MMA initialises the accumulator columns: the first stage of the (single) 3x3
+        // segment, or -- two segments -- the first residual slab, which spans all columns
+        const uint32_t first0 = lead ? (is_res ? (uint32_t)sidx : 1u) : ((uint32_t)si.wstage | (is_res ? 1u : 0u));
+        if (RESW) {
+          // resident weights: nothing to wait for between the taps -- the whole slab is issued from one
+          // elected region (no per-tap elect / branch / warp sync), one commit at its end
+          if (elect_one()) {
+            if (is_res) {
+              issue_stage(ad_slab, bd, first0);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) issue_stage(ad_slab + (uint32_t)sh[t], bd + (uint32_t)t * w_step, first0 | (uint32_t)t);
+            }
+            tc_commit2(&B->a_empty[ab]);
+            if (s == nslabs - 1) tc_commit2(&B->t_full[tb]);
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < ntap) {
               mbar_wait_cluster(&B->w_full[ws], wph);
               tc_fence_after();
-            }
-            const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
-            const uint32_t bd0 = RESW ? bd : ((w_addr16 + (uint32_t)ws * w_step) | bd_lbo);
-            // the group's first MMA initialises the accumulator columns: the first stage of the (single) 3x3
-            // segment, or -- two segments -- the first residual slab, which spans all columns
-            const uint32_t first = lead ? (is_res ? (uint32_t)sidx : 1u) : ((uint32_t)(si.wstage | t) | (is_res ? 1u : 0u));
-            const bool last_tap = t == ntap - 1;
-            if (elect_one()) {
-              if (fold) {
-#pragma unroll
-                for (int m = 0; m < T / 2; ++m) {
-#pragma unroll
-                  for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16, a_hi, bd0 + k * w_k16, b_hi, idesc2, (first | k) != 0);
-#pragma unroll
-                  for (int k = 0; k < TC_KS / 16; ++k)
-                    tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + A_LO, a_hi, bd0 + k * w_k16 + w_s16, b_hi, idesc, 1u);
-                }
-              } else {
-#pragma unroll
-                for (int m = 0; m < T / 2; ++m) {
-#pragma unroll
-                  for (int pass = 0; pass < 3; ++pass) {   // hi*hi, lo*hi, hi*lo
-#pragma unroll
-                    for (int k = 0; k < TC_KS / 16; ++k)
-                      tc_mma2s(dcol + (uint32_t)(m * cpt), ad0 + m * A_TILE + k * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
-                               bd0 + k * w_k16 + (pass == 2 ? w_s16 : 0), b_hi, idesc, (first | pass | k) != 0);
-                  }
-                }
+              const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
+              const uint32_t bd0 = (w_addr16 + (uint32_t)ws * w_step) | bd_lbo;
+              const bool last_tap = t == ntap - 1;
+              if (elect_one()) {
+                issue_stage(ad0, bd0, first0 | (uint32_t)t);
+                tc_commit2(&B->w_empty[ws]);
+                if (last_tap) tc_commit2(&B->a_empty[ab]);
+                if (last_tap && s == nslabs - 1) tc_commit2(&B->t_full[tb]);
               }
-              if (!RESW) tc_commit2(&B->w_empty[ws]);
-              if (last_tap) tc_commit2(&B->a_empty[ab]);
-              if (last_tap && s == nslabs - 1) tc_commit2(&B->t_full[tb]);
+              __syncwarp();
+              if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
             }
-            __syncwarp();
-            if (RESW) bd += w_step;
-            else if (++ws == TC2_WSTAGES) { ws = 0; wph ^= 1; }
           }
         }
         if (++ab == nsb) { ab = 0; aph ^= 1; }
