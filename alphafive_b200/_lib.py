@@ -64,6 +64,9 @@ _SIGS = {
     "a5_engine_busy": (_I, [_P, C.POINTER(C.c_int32), _P]),
     "a5_engine_finish_move": (_I, [_P, _P, _P, _P]),
     "a5_engine_root_stats": (_I, [_P, _P, _P, _P, _P, _P]),
+    "a5_engine_node_stats": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "a5_engine_tau": (_P, [_P]),
+    "a5_dirichlet_sample": (_I, [C.c_uint64, C.c_float, _I, _I, _P, _P]),
     "a5_engine_table_dump": (_I, [_P, _I, _P, _P, _I, C.POINTER(C.c_int32), _P]),
     "a5_record_stride": (_I, [_I]),
     "a5_net_forward_parts": (_I, [_P, _P, _I, _P, _P, _I, _P]),

@@ -15,6 +15,7 @@ from __future__ import annotations
 import os
 import re
 import struct
+import warnings
 
 import numpy as np
 
@@ -137,7 +138,11 @@ def read_bundle(path: str) -> dict[str, np.ndarray]:
                 continue
             dtype, shape, shard, toff, tsize = _entry(val)
             if dtype != 1 or shard != 0:
-                raise ValueError(f"{key!r}: only DT_FLOAT tensors in shard 0 are supported")
+                # e.g. an int64 global_step: load_pretrained of the reference skips what it cannot use
+                # (network.py:136-160); so does this reader, but it says so
+                warnings.warn(f"checkpoint entry {key.decode()!r} skipped (dtype {dtype}, shard {shard}): "
+                              "only DT_FLOAT tensors of shard 0 are read")
+                continue
             arr = np.frombuffer(bytes(data[toff:toff + tsize]), dtype="<f4").reshape(shape)
             out[key.decode()] = arr.astype(np.float32)
     return out
@@ -157,19 +162,65 @@ def _crc32c_table():
 
 
 _CRC_TAB = None
+_CRC_LANES = 2048          # the data is cut into this many equal chunks that advance in lock-step (numpy)
+
+
+def _crc_tab():
+    global _CRC_TAB
+    if _CRC_TAB is None:
+        _CRC_TAB = np.array(_crc32c_table(), np.uint32)
+    return _CRC_TAB
+
+
+def _zero_op(nbytes: int):
+    """GF(2) matrix (32 column ints) of "feed `nbytes` zero bytes" on the raw CRC register."""
+    tab = _crc_tab()
+    one = [int(tab[(1 << j) & 0xFF]) ^ ((1 << j) >> 8) for j in range(32)]      # one zero byte
+
+    def apply(mat, v):
+        r, j = 0, 0
+        while v:
+            if v & 1:
+                r ^= mat[j]
+            v >>= 1
+            j += 1
+        return r
+
+    result = [1 << j for j in range(32)]
+    sq = one
+    while nbytes:
+        if nbytes & 1:
+            result = [apply(sq, c) for c in result]
+        sq = [apply(sq, c) for c in sq]
+        nbytes >>= 1
+    return result, apply
 
 
 def crc32c(data: bytes) -> int:
-    """CRC-32C (Castagnoli), the checksum of LevelDB tables and bundle entries.  Slicing-by-8 over
-    numpy for the 3 MB tensor file would be faster; one checkpoint per 60 steps does not need it."""
-    global _CRC_TAB
-    if _CRC_TAB is None:
-        _CRC_TAB = _crc32c_table()
-    tab = _CRC_TAB
-    c = 0xFFFFFFFF
-    for b in data:
-        c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    """CRC-32C (Castagnoli), the checksum of LevelDB tables and bundle entries.  The register update is
+    linear over GF(2): the data (zero-padded at the front, which leaves a zero register unchanged) is cut
+    into _CRC_LANES chunks whose registers advance together as numpy vectors, the chunk registers are folded
+    with the "append m zero bytes" operator, and the initial 0xFFFFFFFF is carried through the same way."""
+    n = len(data)
+    tab = _crc_tab()
+    if n < 4 * _CRC_LANES:
+        c = 0xFFFFFFFF
+        for b in data:
+            c = int(tab[(c ^ b) & 0xFF]) ^ (c >> 8)
+        return c ^ 0xFFFFFFFF
+    m = -(-n // _CRC_LANES)
+    buf = np.zeros(_CRC_LANES * m, np.uint8)
+    buf[_CRC_LANES * m - n:] = np.frombuffer(data, np.uint8)
+    cols = buf.reshape(_CRC_LANES, m).T.astype(np.uint32)          # cols[t] = byte t of every chunk
+    reg = np.zeros(_CRC_LANES, np.uint32)
+    for t in range(m):
+        reg = tab[(reg ^ cols[t]) & 0xFF] ^ (reg >> 8)
+    zm, apply = _zero_op(m)
+    acc = 0
+    for r in reg.tolist():
+        acc = apply(zm, acc) ^ r
+    zn, _ = _zero_op(n)
+    return (acc ^ apply(zn, 0xFFFFFFFF)) ^ 0xFFFFFFFF
 
 
 def _masked_crc(data: bytes) -> int:
@@ -206,10 +257,10 @@ def _build_block(entries, restart_interval=16) -> bytes:
     return bytes(out)
 
 
-def _entry_proto(shape, offset: int, size: int, crc: int) -> bytes:
-    """BundleEntryProto: dtype DT_FLOAT, shape, (offset), size, crc32c (masked, fixed32)."""
+def _entry_proto(shape, offset: int, size: int, crc: int, dtype: int = 1) -> bytes:
+    """BundleEntryProto: dtype (1 = DT_FLOAT), shape, (offset), size, crc32c (masked, fixed32)."""
     dims = b"".join(b"\x12" + _put_varint(len(d)) + d for d in (b"\x08" + _put_varint(int(n)) for n in shape))
-    out = b"\x08\x01" + b"\x12" + _put_varint(len(dims)) + dims
+    out = b"\x08" + _put_varint(dtype) + b"\x12" + _put_varint(len(dims)) + dims
     if offset:
         out += b"\x20" + _put_varint(offset)
     out += b"\x28" + _put_varint(size) + b"\x35" + struct.pack("<I", crc)
@@ -233,9 +284,11 @@ def write_bundle(prefix: str, tensors: dict, update_marker: bool = True) -> None
     data = bytearray()
     entries = [(b"", b"\x08\x01\x1a\x02\x08\x01")]              # BundleHeaderProto: num_shards 1, version.producer 1
     for name in names:
-        arr = np.asarray(tensors[name], dtype="<f4")
+        arr = np.asarray(tensors[name])
+        code = {"i8": 9, "i4": 3}.get(arr.dtype.str[1:], 1)          # DT_INT64 / DT_INT32 (e.g. a global_step), else DT_FLOAT
+        arr = arr.astype("<f4") if code == 1 else arr.astype(arr.dtype.newbyteorder("<"))
         raw = arr.tobytes(order="C")
-        entries.append((name.encode(), _entry_proto(arr.shape, len(data), len(raw), _masked_crc(raw))))
+        entries.append((name.encode(), _entry_proto(arr.shape, len(data), len(raw), _masked_crc(raw), code)))
         data += raw
 
     def with_trailer(block: bytes) -> bytes:
@@ -251,12 +304,22 @@ def write_bundle(prefix: str, tensors: dict, update_marker: bool = True) -> None
     out += with_trailer(index_block)
     footer = _put_varint(meta_off) + _put_varint(len(meta_block)) + _put_varint(index_off) + _put_varint(len(index_block))
     out += footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", _TABLE_MAGIC)
-    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
-        f.write(bytes(data))
-    with open(prefix + ".index", "wb") as f:
-        f.write(bytes(out))
+    folder = os.path.dirname(os.path.abspath(prefix))
+    os.makedirs(folder, exist_ok=True)
+
+    def put(path, payload, mode):
+        tmp = f"{path}.tmp{os.getpid()}"                      # readers never see a half-written file
+        with open(tmp, mode) as f:
+            f.write(payload)
+        os.replace(tmp, path)
+
+    put(prefix + ".data-00000-of-00001", bytes(data), "wb")
+    put(prefix + ".index", bytes(out), "wb")                  # the index last: it is what restore() looks for
     if update_marker:
         base = os.path.basename(prefix)
-        with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
-            f.write(f'model_checkpoint_path: "{base}"\nall_model_checkpoint_paths: "{base}"\n')
+        marker = os.path.join(folder, "checkpoint")
+        older = []
+        if os.path.exists(marker):                            # tf.train.Saver keeps the last max_to_keep = 5 paths
+            older = [m for m in re.findall(r'all_model_checkpoint_paths:\s*"([^"]+)"', open(marker).read()) if m != base]
+        paths = (older + [base])[-5:]
+        put(marker, f'model_checkpoint_path: "{base}"\n' + "".join(f'all_model_checkpoint_paths: "{m}"\n' for m in paths), "w")

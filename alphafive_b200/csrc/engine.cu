@@ -62,6 +62,74 @@ __device__ __forceinline__ unsigned long long step_now() {
   return t;
 }
 
+// --------------------------------------------------------------------------- //
+// Dirichlet(alpha) numerators (player.py:240), shared by the tree pass and the sampler export
+// --------------------------------------------------------------------------- //
+// Gamma(alpha < 1): Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha).  One attempt, branch-free
+// (acceptance ~96 %): every draw is addressed by (event counter, cell, attempt) in the Philox stream.
+// Fast-math intrinsics: the variates only feed exploration noise (parity there is distributional).
+__device__ __forceinline__ float gamma_try(const Philox& rng, unsigned long long ctr, float d, float c, float inv_alpha,
+                                           int cell, uint32_t attempt, bool* ok) {
+  const uint4 r = rng((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)cell, attempt);
+  const float x = __fsqrt_rn(-2.0f * __logf(u01(r.x))) * __cosf(6.283185307179586f * u01(r.y));
+  const float v1 = 1.0f + c * x;
+  const float v = v1 * v1 * v1;
+  const float u = u01(r.z);
+  const float x2 = x * x;
+  // squeeze u < 1 - 0.0331 x^4, else the full log test (NaN for v <= 0 compares false)
+  const bool acc = u < 1.0f - 0.0331f * x2 * x2 || __logf(u) < 0.5f * x2 + d - d * v + d * __logf(v);
+  *ok = v1 > 0.0f && acc;
+  return d * v * exp2f(__log2f(u01(r.w)) * inv_alpha);
+}
+
+// Numerators for the NCH cells of this lane.  Attempt 0 of every cell runs as NCH independent
+// instruction streams; the ~4 % rejected (lane, cell) pairs of the warp are then compacted -- the j-th
+// reject is retried by lane j -- so the retries cost one more stream instead of NCH (a per-lane retry
+// loop costs the whole warp a latency chain per round, and some lane nearly always rejects).
+template <int NCH>
+__device__ __forceinline__ void gamma_cells(const Philox& rng, unsigned long long ctr, int lane, float alpha,
+                                            const bool (&legal)[NCH], float (&gam)[NCH]) {
+  const float d = alpha + 1.0f - 1.0f / 3.0f;
+  const float c = rsqrtf(9.0f * d);
+  const float inv_alpha = 1.0f / alpha;
+  unsigned rej[NCH];
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    bool ok0;
+    const float g0 = gamma_try(rng, ctr, d, c, inv_alpha, k * 32 + lane, 0u, &ok0);
+    gam[k] = legal[k] ? g0 : 0.0f;
+    rej[k] = __ballot_sync(FULL, legal[k] && !ok0);
+    total += __popc(rej[k]);
+  }
+  for (int base = 0; base < total; base += 32) {           // rounds of 32 rejects (one round in practice)
+    const int j = base + lane;                             // the reject this lane retries
+    int cell = -1, cum = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int n = __popc(rej[k]);
+      if (cell < 0 && j < cum + n) cell = k * 32 + (int)__fns(rej[k], 0, j - cum + 1);
+      cum += n;
+    }
+    float val = d;
+    if (cell >= 0) {
+      bool ok = false;
+      for (uint32_t attempt = 1; !ok && attempt < 24; ++attempt) {
+        const float gv = gamma_try(rng, ctr, d, c, inv_alpha, cell, attempt, &ok);
+        if (ok) val = gv;
+      }
+    }
+    cum = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int src = cum + __popc(rej[k] & ((1u << lane) - 1u)) - base;   // who retried (lane, k)
+      const float got = __shfl_sync(FULL, val, src & 31);
+      if (((rej[k] >> lane) & 1u) && src >= 0 && src < 32) gam[k] = got;
+      cum += __popc(rej[k]);
+    }
+  }
+}
+
 template <int NCH>
 struct Warp {
   const EP& P;
@@ -271,68 +339,6 @@ struct Warp {
     return res;
   }
 
-  // Gamma(alpha < 1): Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha).  One attempt, branch-free
-  // (acceptance ~96 %): every draw is addressed by (event counter, cell, attempt) in the Philox stream.
-  // Fast-math intrinsics: the variates only feed exploration noise (parity there is distributional).
-  __device__ __forceinline__ float gamma_try(float d, float c, float inv_alpha, int cell, uint32_t attempt, bool* ok) const {
-    const uint4 r = rng((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)cell, attempt);
-    const float x = __fsqrt_rn(-2.0f * __logf(u01(r.x))) * __cosf(6.283185307179586f * u01(r.y));
-    const float v1 = 1.0f + c * x;
-    const float v = v1 * v1 * v1;
-    const float u = u01(r.z);
-    const float x2 = x * x;
-    // squeeze u < 1 - 0.0331 x^4, else the full log test (NaN for v <= 0 compares false)
-    const bool acc = u < 1.0f - 0.0331f * x2 * x2 || __logf(u) < 0.5f * x2 + d - d * v + d * __logf(v);
-    *ok = v1 > 0.0f && acc;
-    return d * v * exp2f(__log2f(u01(r.w)) * inv_alpha);
-  }
-
-  // Dirichlet numerators for the NCH cells of this lane.  Attempt 0 of every cell runs as NCH independent
-  // instruction streams; the ~4 % rejected (lane, cell) pairs of the warp are then compacted -- the j-th
-  // reject is retried by lane j -- so the retries cost one more stream instead of NCH (a per-lane retry
-  // loop costs the whole warp a latency chain per round, and some lane nearly always rejects).
-  __device__ __forceinline__ void gamma_cells(float alpha, const bool (&legal)[NCH], float (&gam)[NCH]) const {
-    const float d = alpha + 1.0f - 1.0f / 3.0f;
-    const float c = rsqrtf(9.0f * d);
-    const float inv_alpha = 1.0f / alpha;
-    unsigned rej[NCH];
-    int total = 0;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      bool ok0;
-      const float g0 = gamma_try(d, c, inv_alpha, k * 32 + lane, 0u, &ok0);
-      gam[k] = legal[k] ? g0 : 0.0f;
-      rej[k] = __ballot_sync(FULL, legal[k] && !ok0);
-      total += __popc(rej[k]);
-    }
-    for (int base = 0; base < total; base += 32) {           // rounds of 32 rejects (one round in practice)
-      const int j = base + lane;                             // the reject this lane retries
-      int cell = -1, cum = 0;
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const int n = __popc(rej[k]);
-        if (cell < 0 && j < cum + n) cell = k * 32 + (int)__fns(rej[k], 0, j - cum + 1);
-        cum += n;
-      }
-      float val = d;
-      if (cell >= 0) {
-        bool ok = false;
-        for (uint32_t attempt = 1; !ok && attempt < 24; ++attempt) {
-          const float gv = gamma_try(d, c, inv_alpha, cell, attempt, &ok);
-          if (ok) val = gv;
-        }
-      }
-      cum = 0;
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const int src = cum + __popc(rej[k] & ((1u << lane) - 1u)) - base;   // who retried (lane, k)
-        const float got = __shfl_sync(FULL, val, src & 31);
-        if (((rej[k] >> lane) & 1u) && src >= 0 && src < 32) gam[k] = got;
-        cum += __popc(rej[k]);
-      }
-    }
-  }
-
   // player.py:230-279.  `nd` is the node of the position in sb.  Returns the chosen cell.
   __device__ int select(uint8_t* nd, bool is_root) {
     int32_t* hd = hdr(nd);
@@ -359,7 +365,7 @@ struct Warp {
       gam[k] = 0.0f;
     }
     if (P.training) {
-      gamma_cells(P.alpha, legal, gam);
+      gamma_cells<NCH>(rng, ctr, lane, P.alpha, legal, gam);
 #pragma unroll
       for (int k = 0; k < NCH; ++k) gsum += gam[k];
       gsum = warp_sum(gsum);
@@ -583,9 +589,15 @@ struct Warp {
   __device__ void emit_game(int L, int code) {
     int base = 0;
     if (lane == 0) {
-      base = atomicAdd(&P.out_count[0], L);
-      if (base + L > P.rec_cap) { atomicAdd(&P.out_count[2], L); atomicSub(&P.out_count[0], L); base = -1; }
-      else atomicAdd(&P.out_count[1], 1);
+      // reserve L contiguous records; the counter only ever moves forward by committed games (a reservation
+      // that does not fit is never added, so no rollback can hand two warps overlapping ranges)
+      int old = *(volatile int32_t*)&P.out_count[0];
+      while (true) {
+        if (old + L > P.rec_cap) { atomicAdd(&P.out_count[2], L); base = -1; break; }
+        const int prev = atomicCAS(&P.out_count[0], old, old + L);
+        if (prev == old) { base = old; atomicAdd(&P.out_count[1], 1); break; }
+        old = prev;
+      }
     }
     base = __shfl_sync(FULL, base, 0);
     st[6] += 1;
@@ -860,8 +872,8 @@ __global__ void __launch_bounds__(WPB * 32) k_finish_move(const __grid_constant_
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(WPB * 32) k_root_stats(const __grid_constant__ EP P, int32_t* dn, float* dw,
-                                                        float* dp, int32_t* dsum) {
+__global__ void __launch_bounds__(WPB * 32) k_node_stats(const __grid_constant__ EP P, const int8_t* boards, int32_t* dn,
+                                                        float* dw, float* dp, int32_t* dsum) {
   __shared__ __align__(16) int8_t s_board[WPB][256];
   __shared__ __align__(16) float s_f[WPB][256];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -869,7 +881,8 @@ __global__ void __launch_bounds__(WPB * 32) k_root_stats(const __grid_constant__
   if (g >= P.N) return;
   Warp<NCH> W(P, g, lane, s_board[wid], s_f[wid]);
   int8_t* sb = W.sb;
-  for (int c = lane; c < P.KB; c += 32) sb[c] = P.root_board[(size_t)g * P.KB + c];
+  for (int c = lane; c < P.KB; c += 32)
+    sb[c] = boards ? (c < P.C ? boards[(size_t)g * P.C + c] : 0) : P.root_board[(size_t)g * P.KB + c];
   __syncwarp();
   uint32_t own[NCH], opp[NCH];
   W.board_masks(own, opp);
@@ -883,6 +896,28 @@ __global__ void __launch_bounds__(WPB * 32) k_root_stats(const __grid_constant__
     if (dp) dp[(size_t)g * P.C + c] = lg ? W.edge_p(nd)[c] : 0.0f;
   }
   if (lane == 0 && dsum) dsum[g] = nd ? W.hdr(nd)[0] : -1;
+}
+
+// Sampler export: draw i = one Dirichlet(alpha) vector over the first n_legal cells from Philox stream i,
+// through the same gamma_cells the tree pass calls (distribution tests; player.py:240).
+template <int NCH>
+__global__ void __launch_bounds__(128) k_dirichlet(unsigned long long seed, float alpha, int n_legal, int n_draws, float* eta) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n_draws) return;
+  Philox rng(seed, (unsigned long long)i);
+  bool legal[NCH];
+  float gam[NCH];
+  float gsum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) legal[k] = k * 32 + lane < n_legal;
+  gamma_cells<NCH>(rng, 1ull, lane, alpha, legal, gam);
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) gsum += gam[k];
+  gsum = warp_sum(gsum);
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+    if (legal[k]) eta[(size_t)i * n_legal + k * 32 + lane] = (float)((double)gam[k] / (double)gsum);
 }
 
 template <int NCH>
@@ -949,6 +984,7 @@ struct a5_engine {
   long long* d_stats = nullptr;
   int32_t* h_pinned = nullptr;
   long long* h_stats = nullptr;
+  long long harvest_dropped = 0;   // records a harvest could not return (max_records too small)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1069,6 +1105,7 @@ int a5_engine_reset(a5_engine* e, void* stream) {
   A5_ARG(e);
   cudaStream_t st = (cudaStream_t)stream;
   A5_CUDA(cudaMemsetAsync(e->p.out_count, 0, 16, st));
+  e->harvest_dropped = 0;
   DISPATCH(k_reset, ngrid(e), WPB * 32, st, e->p);
   return A5_OK;
 }
@@ -1126,7 +1163,25 @@ int a5_engine_finish_move(a5_engine* e, float* d_policy, int32_t* d_action, void
 
 int a5_engine_root_stats(a5_engine* e, int32_t* d_n, float* d_w, float* d_p, int32_t* d_sum_n, void* stream) {
   A5_ARG(e);
-  DISPATCH(k_root_stats, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_n, d_w, d_p, d_sum_n);
+  DISPATCH(k_node_stats, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, (const int8_t*)nullptr, d_n, d_w, d_p, d_sum_n);
+  return A5_OK;
+}
+
+int a5_engine_node_stats(a5_engine* e, const int8_t* d_boards, int32_t* d_n, float* d_w, float* d_p, int32_t* d_sum_n,
+                         void* stream) {
+  A5_ARG(e && d_boards);
+  DISPATCH(k_node_stats, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_boards, d_n, d_w, d_p, d_sum_n);
+  return A5_OK;
+}
+
+double* a5_engine_tau(a5_engine* e) { return e ? e->p.tau : nullptr; }
+
+int a5_dirichlet_sample(uint64_t seed, float alpha, int n_legal, int n_draws, float* d_eta, void* stream) {
+  A5_ARG(d_eta && n_legal > 0 && n_legal <= 256 && n_draws > 0 && alpha > 0.0f);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_legal <= 128) k_dirichlet<4><<<(n_draws + 3) / 4, 128, 0, st>>>(seed, alpha, n_legal, n_draws, d_eta);
+  else k_dirichlet<8><<<(n_draws + 3) / 4, 128, 0, st>>>(seed, alpha, n_legal, n_draws, d_eta);
+  A5_CUDA(cudaGetLastError());
   return A5_OK;
 }
 
@@ -1146,13 +1201,22 @@ int a5_engine_harvest(a5_engine* e, void* d_out, int max_records, int32_t* h_cou
   cudaStream_t st = (cudaStream_t)stream;
   A5_CUDA(cudaMemcpyAsync(e->h_pinned + 8, e->p.out_count, 12, cudaMemcpyDeviceToHost, st));
   A5_CUDA(cudaStreamSynchronize(st));
-  int cnt = e->h_pinned[8], games = e->h_pinned[9];
-  int ncopy = cnt < max_records ? cnt : max_records;
+  const int cnt = e->h_pinned[8], games = e->h_pinned[9], arena_full = e->h_pinned[10];
+  const int ncopy = cnt < max_records ? cnt : max_records;
   if (ncopy > 0)
     A5_CUDA(cudaMemcpyAsync(d_out, e->p.out_rec, (size_t)ncopy * e->p.rec_stride, cudaMemcpyDeviceToDevice, st));
-  A5_CUDA(cudaMemsetAsync(e->p.out_count, 0, 8, st));
+  A5_CUDA(cudaMemsetAsync(e->p.out_count, 0, 12, st));
+  const int lost = arena_full + (cnt - ncopy);     // plies of games that found the arena full + plies cut off here
+  e->harvest_dropped += lost;
   *h_count = ncopy;
   if (h_games) *h_games = games;
+  if (lost > 0) {
+    // whole games are lost, never parts of one (emit_game reserves a game's plies atomically), but the
+    // replay buffer would silently miss them: the caller must harvest more often or raise record_capacity
+    set_error("a5_engine_harvest: %d finished-ply records lost (%d did not fit the record arena of %d, %d beyond "
+              "max_records = %d)", lost, arena_full, e->p.rec_cap, cnt - ncopy, max_records);
+    return A5_ERR_CAPACITY;
+  }
   return A5_OK;
 }
 
@@ -1166,7 +1230,7 @@ int a5_engine_counters(a5_engine* e, int64_t* h_out, void* stream) {
   A5_CUDA(cudaMemcpyAsync(e->h_pinned + 12, e->p.out_count + 2, 4, cudaMemcpyDeviceToHost, st));
   A5_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < A5_NUM_COUNTERS; ++i) h_out[i] = i < GS ? e->h_stats[i] : 0;
-  h_out[10] += e->h_pinned[12];
+  h_out[10] += e->h_pinned[12] + e->harvest_dropped;
   if (h_out[8] > 0) {
     set_error("a5_engine: %lld leaf expansions did not fit the per-game node arena (node_capacity=%d)",
               (long long)h_out[8], e->p.cap);

@@ -53,7 +53,17 @@ def label_result(game_record) -> int:
 
 def gen_data(pipe, q, config=None, games=None, seed=0):
     """One reference-style worker: ``Player(config, training=True, pipe=pipe).run()`` forever
-    (or ``games`` times), each game put on ``q`` as ``(record, result)``."""
+    (or ``games`` times), each game put on ``q`` as ``(record, result)``.
+
+    The worker creates a CUDA engine, and CUDA cannot be used in a *forked* child of a process that has
+    already initialised it (main.py:50-55 forks after building the network): start these workers with
+    ``multiprocessing.get_context("spawn").Process(target=gen_data, ...)``, or use ``gen_data_lockstep``
+    (one process, thousands of games), which is what ``train_loop`` does."""
+    import multiprocessing as mp
+    if mp.current_process().name != "MainProcess" and mp.get_start_method(allow_none=True) in (None, "fork") \
+            and torch.cuda.is_initialized():
+        raise RuntimeError("gen_data: forked after CUDA was initialised in the parent; start the worker with the "
+                           "'spawn' start method (or use gen_data_lockstep)")
     if config is None:
         from . import config as config_module
         config = config_module
@@ -88,7 +98,7 @@ def train_loop(config, n_games=4096, total_step=None, restore=None, seed=0, save
     the shared session).  Returns (trainer, stack, step)."""
     import numpy as np
     from .genData.network import ResNet
-    from .replay import HEADER_BYTES
+    from .replay import parse_headers
     from .selfplay import SelfPlay
     from .train import Trainer
     from .utils import RandomStack
@@ -107,9 +117,8 @@ def train_loop(config, n_games=4096, total_step=None, restore=None, seed=0, save
         records, _ = sp.harvest()
         if records.shape[0] == 0:
             continue
-        head = records[:, :HEADER_BYTES].cpu().numpy()
-        lens = head[:, 14:16].copy().view(np.int16).reshape(-1)
-        res = head[:, 28:32].copy().view(np.int32).reshape(-1)
+        head = parse_headers(records)
+        lens, res = head["game_len"], head["result"]
         i = 0
         while i < records.shape[0] and step < total_step:
             n = int(lens[i])

@@ -115,6 +115,20 @@ class SearchEngine:
         check(self.lib.a5_engine_root_stats(self.handle, ptr(n), ptr(w), ptr(p), ptr(s), stream_ptr()))
         return n, w, p, s
 
+    def node_stats(self, boards):
+        """(n, w, p, sum_n) of the table node of ``boards[i]`` in game i (sum_n = -1 if absent)."""
+        boards = torch.as_tensor(boards, dtype=torch.int8).to(self.device).contiguous()
+        n = torch.empty((self.N, self.C), dtype=torch.int32, device=self.device)
+        w = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        p = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+        s = torch.empty((self.N,), dtype=torch.int32, device=self.device)
+        check(self.lib.a5_engine_node_stats(self.handle, ptr(boards), ptr(n), ptr(w), ptr(p), ptr(s), stream_ptr()))
+        return n, w, p, s
+
+    def tau(self) -> torch.Tensor:
+        """Zero-copy float64 [N] view of every game's temperature (Player.tau)."""
+        return _view(self.lib.a5_engine_tau(self.handle), (self.N,), torch.float64, self.device)
+
     def table_dump(self, game: int, max_nodes: int = 65536):
         boards = torch.empty((max_nodes, self.S, self.S), dtype=torch.int8, device=self.device)
         sums = torch.empty((max_nodes,), dtype=torch.int32, device=self.device)
@@ -191,7 +205,7 @@ class SearchEngine:
 
 class _DevView:
     """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
-    _TYPES = {torch.int8: "|i1", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4"}
+    _TYPES = {torch.int8: "|i1", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8"}
 
     def __init__(self, p, shape, dtype):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": self._TYPES[dtype],
@@ -200,6 +214,13 @@ class _DevView:
 
 def _view(p, shape, dtype, device) -> torch.Tensor:
     return torch.as_tensor(_DevView(p, shape, dtype), device=device)
+
+
+def dirichlet_sample(seed: int, alpha: float, n_legal: int, n_draws: int) -> torch.Tensor:
+    """n_draws Dirichlet(alpha) vectors over n_legal cells from the tree pass's sampler (a5_dirichlet_sample)."""
+    eta = torch.empty((n_draws, n_legal), dtype=torch.float32, device="cuda")
+    check(_lib.load().a5_dirichlet_sample(seed, alpha, n_legal, n_draws, ptr(eta), stream_ptr()))
+    return eta
 
 
 from .replay import parse_records  # noqa: E402,F401  (kept importable from here)

@@ -13,11 +13,13 @@ evaluation stays on the device.
 from __future__ import annotations
 
 import gc
+from collections.abc import Mapping
 
 import numpy as np
 import torch
 
 from .. import rules
+from .._lib import A5Error
 from ..engine import SearchEngine, make_config
 
 
@@ -51,6 +53,57 @@ def state_to_board(state: str, board_size: int) -> np.ndarray:
     return board
 
 
+class Action(object):
+    """Edge statistics as the reference holds them (player.py:9-14); read-only copy of the device node."""
+    __slots__ = ("n", "w", "q", "p")
+
+    def __init__(self, n=0, w=0.0, p=0.0):
+        self.n, self.w, self.p = n, w, p
+        self.q = w / n if n else 0
+
+
+class State(object):
+    """Node as the reference holds it (player.py:17-20): ``a`` maps every legal (i, j) to its Action."""
+    __slots__ = ("a", "sum_n")
+
+    def __init__(self, a, sum_n):
+        self.a, self.sum_n = a, sum_n
+
+
+class _TreeView(Mapping):
+    """Read-only ``Player.tree`` (player.py:29): state string -> State, fetched from the device table on
+    access (a5_engine_table_dump for the keys, a5_engine_node_stats for a node)."""
+
+    def __init__(self, engine, S):
+        self._eng, self._S = engine, S
+        self._keys = None
+
+    def _load(self):
+        if self._keys is None:
+            boards, sums = ([], []) if self._eng is None else self._eng.table_dump(0)
+            self._keys = {board_to_state(b): int(s) for b, s in zip(boards, sums)}
+        return self._keys
+
+    def __len__(self):
+        return len(self._load())
+
+    def __iter__(self):
+        return iter(self._load())
+
+    def __contains__(self, state):
+        return state in self._load()
+
+    def __getitem__(self, state):
+        if state not in self._load():
+            raise KeyError(state)
+        S = self._S
+        board = state_to_board(state, S)
+        n, w, p, s = [t.cpu().numpy()[0] for t in self._eng.node_stats(board[None])]
+        a = {(c // S, c % S): Action(int(n[c]), np.float32(w[c]), np.float32(p[c]))
+             for c in np.flatnonzero(board.reshape(-1) == 0)}
+        return State(a, int(s))
+
+
 class Player(object):
     def __init__(self, cfg=None, training=True, pipe=None, pv_fn=None, seed=0):
         assert pipe is not None or pv_fn is not None
@@ -70,11 +123,19 @@ class Player(object):
     # ------------------------------------------------------------------ engine plumbing
     def _eng(self) -> SearchEngine:
         cfg = self.config
-        if self._engine is None or self._engine.S != cfg.board_size:
-            self._engine = SearchEngine(make_config(cfg, n_games=1, training=self.training, seed=self._seed))
-            self._clear = True
         budget = (cfg.simulation_per_step, cfg.upper_simulation_per_step)
-        if budget != self._budget:                   # config is read lazily (choose_best_player.py:25)
+        # the table holds the retained sub-tree (at most ~upper nodes: its root was selected from that often)
+        # plus this move's expansions; sized from the budget in force and re-created (tree dropped, like a
+        # reset) if the caller raises config.simulation_per_step past it (choose_best_player.py:25 mutates it)
+        need = min(max(2 * budget[0], budget[0] + budget[1]) + 1024, 32768)
+        if self._engine is None or self._engine.S != cfg.board_size or need > self._engine.cfg.node_capacity:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = SearchEngine(make_config(cfg, n_games=1, training=self.training, seed=self._seed,
+                                                    node_capacity=need))
+            self._clear = True
+            self._budget = None
+        if budget != self._budget:                   # config is read lazily
             self._engine.set_budget(*budget)
             self._budget = budget
         return self._engine
@@ -103,17 +164,22 @@ class Player(object):
         return (chr(ord("a") + self.config.board_size) + "/") * self.config.board_size
 
     def reset(self, search_tree=None):
+        """player.py:48-51.  The table lives on the device: a caller-supplied dict of State objects cannot
+        be adopted, so anything but ``None`` is an error rather than being silently ignored."""
+        if search_tree is not None:
+            raise NotImplementedError("Player.reset(search_tree=...): the search table is device-resident; "
+                                      "only reset() / reset(None) is supported")
         self._clear = True
         self.root_state = None
         self.tau = self.config.init_temp
 
     @property
     def tree(self):
-        """Snapshot {state string: sum_n} of the device table (the reference exposes its dict)."""
+        """The transposition table as the reference exposes it (player.py:29): a read-only mapping
+        state string -> State(a = {(i, j): Action(n, w, q, p)}, sum_n), read from the device on access."""
         if self._engine is None or self._clear:
-            return {}
-        boards, sums = self._engine.table_dump(0)
-        return {board_to_state(b): int(s) for b, s in zip(boards, sums)}
+            return _TreeView(None, self.config.board_size)
+        return _TreeView(self._engine, self.config.board_size)
 
     def get_action(self, state: str, e: float = 0.25, last_action: tuple = None, random_a=False):
         eng = self._eng()
@@ -127,6 +193,11 @@ class Player(object):
         self._clear = False
         net, fn = self._leaf_fn()
         eng.run_search(net=net, pv_fn=fn, check_every=8)
+        try:
+            eng.counters()                            # raises A5_ERR_CAPACITY if an expansion did not fit
+        except A5Error as err:
+            raise A5Error(f"Player.get_action: search table overflow ({err}); visit counts would diverge "
+                          "from the reference") from None
         policy, action = eng.finish_move()
         a = int(action.cpu()[0])
         act = (a // S, a % S)
@@ -162,9 +233,11 @@ class Player(object):
         return out
 
     def pruning_tree(self, board: np.ndarray, state: str = None):
-        """The reference deletes ancestors of ``board`` here (player.py:149-164).  The device
-        table is garbage-collected against the root at every get_action, which removes a
-        superset of those keys, so there is nothing left to do."""
+        """The reference deletes the same-perspective ancestors of ``board`` here (player.py:149-164:
+        keys != state whose +1 stones and -1 stones are subsets of the board's).  The device table is
+        garbage-collected against the root at every get_action -- only positions containing all of the
+        root's stones survive -- which removes a superset of those keys (tests/test_gpu_facade.py), so there
+        is nothing left to delete."""
         return None
 
     def close(self):

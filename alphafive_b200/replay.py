@@ -71,20 +71,36 @@ def allreduce_wins(wins0: int, wins1: int, draws: int, group=None, device=None):
 # ---------------------------------------------------------------------------------------
 # record bytes -> the reference's replay tuples (player.py:77-82) and back
 # ---------------------------------------------------------------------------------------
+HEADER_DTYPE = np.dtype([("game_id", "<i8"), ("game_serial", "<i4"), ("ply", "<i2"), ("game_len", "<i2"),
+                         ("last_action", "<i4"), ("value", "<f4"), ("weight", "<f4"), ("result", "<i4")])
+assert HEADER_DTYPE.itemsize == HEADER_BYTES
+
+
+def parse_headers(buf) -> np.ndarray:
+    """The a5_record_header of every record as one structured array (one D2H copy of 32 B per record)."""
+    if isinstance(buf, torch.Tensor):
+        buf = buf[:, :HEADER_BYTES].contiguous().cpu().numpy()
+    else:
+        buf = np.ascontiguousarray(np.asarray(buf)[:, :HEADER_BYTES])
+    return buf.view(HEADER_DTYPE).reshape(-1)
+
+
 def parse_records(buf, S: int):
     """uint8 [count, stride] (torch or numpy) -> list of dicts with numpy fields."""
     host = buf.cpu().numpy() if isinstance(buf, torch.Tensor) else np.asarray(buf)
     Cc = S * S
     bb = (Cc + 15) // 16 * 16
-    out = []
-    for row in host:
-        h = RecordHeader.from_buffer_copy(row[:HEADER_BYTES].tobytes())
-        board = row[HEADER_BYTES:HEADER_BYTES + Cc].view(np.int8).reshape(S, S).copy()
-        policy = row[HEADER_BYTES + bb:HEADER_BYTES + bb + 4 * Cc].view(np.float32).reshape(S, S).copy()
-        out.append(dict(game_id=h.game_id, game_serial=h.game_serial, ply=h.ply, game_len=h.game_len,
-                        last_action=h.last_action, value=h.value, weight=h.weight, result=h.result,
-                        board=board, policy=policy))
-    return out
+    n = host.shape[0]
+    if n == 0:
+        return []
+    head = parse_headers(host)
+    boards = np.ascontiguousarray(host[:, HEADER_BYTES:HEADER_BYTES + Cc]).view(np.int8).reshape(n, S, S)
+    policies = np.ascontiguousarray(host[:, HEADER_BYTES + bb:HEADER_BYTES + bb + 4 * Cc]).view(np.float32).reshape(n, S, S)
+    cols = {k: head[k].tolist() for k in HEADER_DTYPE.names}
+    return [dict(game_id=cols["game_id"][i], game_serial=cols["game_serial"][i], ply=cols["ply"][i],
+                 game_len=cols["game_len"][i], last_action=cols["last_action"][i],
+                 value=np.float32(cols["value"][i]).item(), weight=np.float32(cols["weight"][i]).item(),
+                 result=cols["result"][i], board=boards[i], policy=policies[i]) for i in range(n)]
 
 
 def pack_records(recs, S: int) -> np.ndarray:

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .replay import HEADER_BYTES, pack_records, parse_records, record_stride
+from .replay import HEADER_BYTES, pack_records, parse_headers, parse_records, record_stride
 
 BLACK_WIN, WHITE_WIN, DRAW = 1, -1, 0
 
@@ -109,15 +109,11 @@ class RandomStack:
         a game are contiguous and ordered as the engine emits them).  Returns the accept flags."""
         if records.shape[0] == 0:
             return []
-        host = records[:, :HEADER_BYTES].cpu().numpy()
-        lens = host[:, 14:16].copy().view(np.int16).reshape(-1)      # game_len
-        res = host[:, 28:32].copy().view(np.int32).reshape(-1)       # result
-        out, i = [], 0
-        while i < records.shape[0]:
-            n = int(lens[i])
-            out.append(self.push(records[i:i + n], int(res[i])))
-            i += n
-        return out
+        head = parse_headers(records)                           # one 32 B/record D2H copy for the whole harvest
+        starts = np.flatnonzero(head["ply"] == 0)
+        lens, res = head["game_len"][starts].tolist(), head["result"][starts].tolist()
+        assert sum(lens) == records.shape[0], "records are not whole games with contiguous plies"
+        return [self.push(records[i:i + n], r) for i, n, r in zip(starts.tolist(), lens, res)]
 
     def get_data(self, batch_size=1):
         """utils.py:118-146 -> (boards f32[n,3,S,S], weights f32[n], values f32[n], policies f32[n,S*S])
@@ -130,11 +126,12 @@ class RandomStack:
         S = self.board_size
         num = min(batch_size, self.count)
         idx = np.random.choice(self.count, size=num, replace=False)
-        rot = np.empty(num, np.uint8)
-        flip = np.empty(num, np.uint8)
-        for i in range(num):                                    # the reference's draw order (utils.py:128,136)
-            rot[i] = np.random.choice([0, 1, 2, 3])
-            flip[i] = random.choice([1, 2]) == 1
+        # utils.py:128,136 draw a rotation (numpy stream) and a flip (Python stream) per sample.  The two
+        # streams are independent, and legacy np.random.choice over a 4-element list is one bounded 32-bit draw,
+        # so one bulk randint consumes the numpy stream exactly like the reference's per-sample calls
+        # (tests/test_gpu_replay_stack.py compares batches with the real RandomStack under equal seeds)
+        rot = np.random.randint(0, 4, size=num).astype(np.uint8)
+        flip = np.fromiter((random.choice((1, 2)) == 1 for _ in range(num)), np.uint8, num)
         return self.gather((self.head + idx.astype(np.int64)) % self.capacity, rot, flip)
 
     def gather(self, rows, rot, flip):

@@ -31,7 +31,7 @@ typedef enum {
   A5_ERR_ARG = -1,               /* bad argument                                  */
   A5_ERR_CUDA = -2,              /* CUDA runtime error (see a5_last_error)        */
   A5_ERR_STATE = -3,             /* call not valid in the engine's current mode   */
-  A5_ERR_CAPACITY = -4           /* a per-game node arena overflowed              */
+  A5_ERR_CAPACITY = -4           /* a per-game node arena or the record arena overflowed */
 } a5_status;
 
 int a5_version(void);
@@ -146,6 +146,20 @@ int a5_engine_finish_move(a5_engine* e, float* d_policy, int32_t* d_action, void
  * n int32[N][S*S], w f32, p f32, sum_n int32[N]; any pointer may be NULL. */
 int a5_engine_root_stats(a5_engine* e, int32_t* d_n, float* d_w, float* d_p, int32_t* d_sum_n, void* stream);
 
+/* The same for the node of an arbitrary position per game (d_boards int8[N][S*S]): what
+ * Player.tree[state].a[action].{n,w,p} / .sum_n hold (player.py:9-20,29); sum_n = -1 and zero rows when the
+ * position is not in game i's table.  Read-only. */
+int a5_engine_node_stats(a5_engine* e, const int8_t* d_boards, int32_t* d_n, float* d_w, float* d_p,
+                         int32_t* d_sum_n, void* stream);
+
+/* Player.tau of every game (player.py:32,108-111): double[N] on the device, decayed by finish_move. */
+double* a5_engine_tau(a5_engine* e);
+
+/* n_draws Dirichlet(alpha * 1_A) vectors, A = n_legal, from the sampler the tree pass uses at every node
+ * visit (np.random.dirichlet, player.py:240); draw i uses Philox stream i of `seed`.  d_eta f32[n_draws][n_legal].
+ * Exists so the distribution of the exploration noise can be tested against Beta(alpha, alpha (A-1)) marginals. */
+int a5_dirichlet_sample(uint64_t seed, float alpha, int n_legal, int n_draws, float* d_eta, void* stream);
+
 /* Table contents of one game: up to max_nodes boards int8[max_nodes][S*S] and their
  * sum_n; returns the number of nodes in *h_count (synchronises). */
 int a5_engine_table_dump(a5_engine* e, int game, int8_t* d_boards, int32_t* d_sum_n, int max_nodes,
@@ -167,7 +181,9 @@ typedef struct {
 
 int a5_record_stride(int S);     /* bytes per ply record                            */
 /* Move up to max_records finished-ply records into d_out (device) and reset the
- * engine's record arena; *h_count = number copied, *h_games = games completed. */
+ * engine's record arena; *h_count = number copied, *h_games = games completed.  A game's plies are
+ * always contiguous and complete.  Returns A5_ERR_CAPACITY (after copying what fits) if games were lost
+ * because the arena was full or max_records was too small; the loss is also counted in counters()[10]. */
 int a5_engine_harvest(a5_engine* e, void* d_out, int max_records, int32_t* h_count, int32_t* h_games, void* stream);
 
 /* Counters since create/reset (synchronises):

@@ -18,6 +18,9 @@ replay_sample.npz    1,024 records + 3 whole games of data_buffer/data6960.pkl
 ckpt6960.npz         the 42 tensors of ckpt/alphaFive-6960 (via alphafive_b200.ckpt)
 ckpt6960_files.npz   the shipped .index file verbatim + sha256 of the .data file (pins the writer)
 weights.npz          construct_weights(L, 0.94) for L = 1..64
+policy_vectors.npz   calc_policy outputs (policy, tau) of the real Player over consecutive moves
+mcts_mix_11.npz      root / depth-1 visit counts of seeded training-mode searches (mix weights)
+selfplay_games_11.npz lengths / results of seeded Player.run() games (training mode)
 replay_stack.npz     utils.RandomStack driven with seeded generators: accept flags and
                      bookkeeping after every push, one get_data batch
 """
@@ -241,6 +244,150 @@ def make_mcts_train(utils, config, Player, salt):
     print("mcts_train_11: min visits", ns.min(), "mean max", ns.max(1).mean(), "depth", depth.mean())
 
 
+
+def make_policy_vectors(utils, config, Player):
+    """calc_policy vectors (player.py:84-126) from the real Player.
+
+    det_*   : Player(training=False).get_action(random_a=True) move after move under the tie-free
+              table pv_fn -- the search is deterministic, so a device engine fed the same roots
+              holds the same visit counts and must return the same policy and tau.  Two sequences:
+              init_temp = 1.2 (soft branch) and init_temp = 0.02 (crosses tau <= 0.01 at call 7).
+    train_* : Player(training=True) seeded: (n, tau) -> policy vectors of the soft branch with
+              noisy visit counts (checked against oracle.mcts.soft_policy on the CPU; the device is
+              compared with that formula on its own counts)."""
+    from oracle.mcts import table_pv_fn
+    S = 11
+    config.board_size = S
+    out = {}
+    keep = (config.simulation_per_step, config.upper_simulation_per_step, config.init_temp)
+    config.simulation_per_step, config.upper_simulation_per_step = 120, 135
+    for tag, temp, plies in (("det_hi", 1.2, 14), ("det_lo", 0.02, 12)):
+        config.init_temp = temp
+        for salt in range(30, 230):
+            np.random.seed(77 + salt); random.seed(77 + salt)
+            pl = Player(config, training=False, pv_fn=table_pv_fn(S, salt))
+            state, action = pl.get_init_state(), None
+            rec = dict(boards=[], last=[], n=[], policy=[], tau=[], action=[], budget=[])
+            ok = True
+            with _TieWatch() as tw:
+                for _ in range(plies):
+                    seen = state in pl.tree
+                    budget = 120 if not seen else min(120, 135 - pl.tree[state].sum_n)
+                    la = action
+                    policy, action = pl.get_action(state, last_action=la, random_a=True)
+                    n = _root_arrays(pl, state, S)[0]
+                    board = utils.state_to_board(state, S)
+                    rec["boards"].append(board.copy()); rec["last"].append(la if la else (-1, -1))
+                    rec["n"].append(n); rec["policy"].append(policy.reshape(-1).copy()); rec["tau"].append(pl.tau)
+                    rec["action"].append(action); rec["budget"].append(budget)
+                    board = utils.step(board, action)
+                    state = utils.board_to_state(board)
+                    if utils.is_game_over(board, 5)[0]:
+                        ok = len(rec["n"]) >= plies
+                        break
+            # ties inside the search would make n irreproducible; ties in the final pick only matter
+            # when tau <= 0.01 (the uniform-over-best policy is still deterministic)
+            if ok and tw.worst == 1:
+                break
+        else:
+            raise AssertionError("no tie-free salt for the policy vectors")
+        out[f"{tag}_salt"] = salt
+        out[f"{tag}_init_temp"] = temp
+        for k, v in rec.items():
+            out[f"{tag}_{k}"] = np.asarray(v)
+        print(f"policy {tag}: salt {salt}, tau {rec['tau'][0]:.4f} .. {rec['tau'][-1]:.5f}, budgets {rec['budget']}")
+    # training mode, seeded
+    config.init_temp = 1.2
+    config.simulation_per_step, config.upper_simulation_per_step = 300, 400
+    np.random.seed(99); random.seed(99)
+    pl = Player(config, training=True, pv_fn=table_pv_fn(S, 9))
+    state, action = pl.get_init_state(), None
+    rec = dict(boards=[], n=[], policy=[], tau=[])
+    for _ in range(12):
+        policy, action = pl.get_action(state, last_action=action)
+        rec["boards"].append(utils.state_to_board(state, S)); rec["n"].append(_root_arrays(pl, state, S)[0])
+        rec["policy"].append(policy.reshape(-1).copy()); rec["tau"].append(pl.tau)
+        board = utils.step(utils.state_to_board(state, S), action)
+        state = utils.board_to_state(board)
+        if utils.is_game_over(board, 5)[0]:
+            break
+    for k, v in rec.items():
+        out[f"train_{k}"] = np.asarray(v)
+    config.simulation_per_step, config.upper_simulation_per_step, config.init_temp = keep
+    np.savez_compressed(os.path.join(OUT, "policy_vectors.npz"), **out)
+    print("policy_vectors: train plies", len(rec["n"]))
+
+
+def _mix_run(args):
+    """One training-mode search of the real Player (300 sims, empty 11x11 board, table policy with
+    zero value): root visit counts and the visit counts of every depth-1 node."""
+    seed, salt, sims = args
+    utils, config, Player = _ref()
+    from oracle.mcts import table_pv_fn
+    S = 11
+    config.board_size = S
+    config.simulation_per_step, config.upper_simulation_per_step = sims, sims + 100
+    np.random.seed(seed); random.seed(seed)
+    pl = Player(config, training=True, pv_fn=table_pv_fn(S, salt, zero_value=True))
+    state = pl.get_init_state()
+    pl.root_state = state
+    for _ in range(sims):
+        pl.MCTS_search(state, [state], None)
+    root_n = _root_arrays(pl, state, S)[0]
+    child_n = np.zeros((S * S, S * S), np.int16)
+    empty = np.zeros((S, S), np.int8)
+    for c in range(S * S):
+        b = utils.step(empty.copy(), (c // S, c % S))
+        st = utils.board_to_state(b)
+        if st in pl.tree:
+            child_n[c] = _root_arrays(pl, st, S)[0]
+    return root_n, child_n
+
+
+def make_mix_stats(runs=96, salt=9, sims=300):
+    """Pins the Dirichlet mixing weights (player.py:247-253): with q == 0 everywhere the second visit of a
+    depth-1 node picks argmax(0.9 p + 0.1 eta) and the post-ladder root picks follow
+    (0.75 p + 0.25 eta) sqrt(sum_n + 1) / (1 + n)."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(8) as pool:
+        res = pool.map(_mix_run, [(5000 + r, salt, sims) for r in range(runs)])
+    np.savez_compressed(os.path.join(OUT, "mcts_mix_11.npz"), salt=salt, sims=sims,
+                        root_n=np.stack([r[0] for r in res]), child_n=np.stack([r[1] for r in res]))
+    print("mcts_mix_11:", runs, "runs")
+
+
+def _game_run(args):
+    seed, salt, sims, upper = args
+    utils, config, Player = _ref()
+    from oracle.mcts import table_pv_fn
+    config.board_size = 11
+    config.simulation_per_step, config.upper_simulation_per_step = sims, upper
+    np.random.seed(seed); random.seed(seed)
+    pl = Player(config, training=True, pv_fn=table_pv_fn(11, salt))
+    rec = pl.run()
+    value = rec[-1][-2]
+    result = utils.DRAW if value == 0.0 else (utils.BLACK_WIN if len(rec) % 2 == 1 else utils.WHITE_WIN)   # main.py:86-93
+    first = rec[1][2]                              # the first move played
+    ent = [float(-(r[1][r[1] > 0] * np.log(r[1][r[1] > 0])).sum()) for r in rec[:8]]
+    return len(rec), result, first[0] * 11 + first[1], ent
+
+
+def make_games(games=400, salt=9, sims=60, upper=80, name="selfplay_games_11.npz"):
+    """Whole self-play games of the real Player.run() (training mode, seeded per game): lengths, results
+    (main.py:86-93), first moves and the policy entropy of the first 8 plies -- distributional pins."""
+    import multiprocessing as mp
+    utils = _ref()[0]
+    with mp.get_context("fork").Pool(8) as pool:
+        res = pool.map(_game_run, [(9000 + g, salt, sims, upper) for g in range(games)], chunksize=1)
+    np.savez_compressed(os.path.join(OUT, name), salt=salt, sims=sims, upper=upper,
+                        length=np.array([r[0] for r in res]), result=np.array([r[1] for r in res]),
+                        first=np.array([r[2] for r in res]), entropy=np.array([r[3] for r in res], np.float32),
+                        codes=np.array([utils.DRAW, utils.BLACK_WIN, utils.WHITE_WIN]))
+    L = np.array([r[0] for r in res]); R = np.array([r[1] for r in res])
+    print(name, games, "games; length mean", L.mean(), "min", L.min(), "max", L.max(),
+          "black", (R == utils.BLACK_WIN).mean(), "white", (R == utils.WHITE_WIN).mean())
+
+
 def make_replay(utils):
     data = pickle.load(open(f"{REF}/data_buffer/data6960.pkl", "rb"))
     lens = pickle.load(open(f"{REF}/data_buffer/data_len6960.pkl", "rb"))
@@ -346,6 +493,19 @@ def main():
     if "--ckpt-only" in sys.argv:
         make_ckpt()
         return
+    if "--policy-only" in sys.argv:
+        make_policy_vectors(*_ref())
+        return
+    if "--mix-only" in sys.argv:
+        make_mix_stats()
+        return
+    if "--games-only" in sys.argv:
+        make_games()
+    make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
+        return
+    if "--games300-only" in sys.argv:
+        make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
+        return
     if "--replay-stack-only" in sys.argv:
         make_replay_stack(_ref()[0])
         return
@@ -373,6 +533,10 @@ def main():
     make_mcts_game(11, utils, config, Player, sims=120, upper=135, plies=14, salt=5)
     make_mcts_game(15, utils, config, Player, sims=60, upper=68, plies=8, salt=6)
     make_mcts_train(utils, config, Player, salt=9)
+    make_policy_vectors(utils, config, Player)
+    make_mix_stats()
+    make_games()
+    make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
 
 
 if __name__ == "__main__":

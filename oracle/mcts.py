@@ -160,10 +160,13 @@ class OraclePlayer:
         a = node.cells.shape[0]
         if self.training:
             eta = self.rng.dirichlet(cfg.dirichlet_alpha * np.ones(a))
+            # mix weights 0.25 at the root / 0.10 elsewhere (player.py:249-253); ``noise_mix`` exists so the
+            # distribution tests can show that they would notice swapped or wrong weights
+            e_root, e_in = getattr(self, "noise_mix", (0.25, 0.1))
             if is_root:
-                pm = (np.float32(0.75) * node.p).astype(np.float64) + 0.25 * eta
+                pm = (np.float32(1 - e_root) * node.p).astype(np.float64) + e_root * eta
             else:
-                pm = (np.float32(0.9) * node.p).astype(np.float64) + 0.1 * eta
+                pm = (np.float32(1 - e_in) * node.p).astype(np.float64) + e_in * eta
             t = cfg.c_puct * pm                                   # float64
         else:
             t = (np.float32(cfg.c_puct) * node.p).astype(np.float64)
@@ -190,13 +193,10 @@ class OraclePlayer:
             return None, best_action
         self.tau *= cfg.tau_decay_rate_r if random_a else cfg.tau_decay_rate
         policy = np.zeros(S * S, np.float32)
-        if self.tau <= 0.01:
-            policy[node.cells[top]] = 1.0 / top.size
-            return policy.reshape(S, S), best_action
-        pv = visits / np.max(visits)
-        pv = np.power(pv, np.float32(1 / self.tau))
-        pv = pv / np.sum(pv)
+        pv = soft_policy(node.n, self.tau)
         policy[node.cells] = pv
+        if self.tau <= 0.01:
+            return policy.reshape(S, S), best_action
         pick = int(node.cells[self.rng.choice(pv.shape[0], p=pv.astype(np.float64) / pv.astype(np.float64).sum())])
         return policy.reshape(S, S), (pick // S, pick % S)
 
@@ -233,6 +233,21 @@ class OraclePlayer:
         return n, w, p, node.sum_n
 
 
+def soft_policy(n_legal, tau) -> np.ndarray:
+    """player.py:112-120 on the visit counts of the legal cells (row-major), with the
+    temperature *after* its decay: tau <= 0.01 -> uniform over the most-visited cells;
+    else float32 ``(n / max n) ** (1 / tau)`` normalised by its float32 sum."""
+    n_legal = np.asarray(n_legal)
+    if tau <= 0.01:
+        top = n_legal == n_legal.max()
+        return np.where(top, np.float32(1.0 / top.sum()), np.float32(0)).astype(np.float32)
+    pv = n_legal.astype(np.float32)
+    pv /= np.max(pv)
+    pv = np.power(pv, 1 / tau)                      # f32 array ** python float -> f32 (NEP 50)
+    pv /= np.sum(pv)
+    return pv
+
+
 def game_result(record) -> int:
     """Outcome label of a finished game as the data-generating worker computes it
     (main.py:86-93): draw if the last stored value is 0, else black wins iff the
@@ -242,35 +257,36 @@ def game_result(record) -> int:
     return rules.BLACK_WIN if len(record) % 2 == 1 else rules.WHITE_WIN
 
 
-def table_pv_fn(size: int, salt: int = 0):
+def table_pv_fn(size: int, salt: int = 0, zero_value: bool = False):
     """A deterministic, transcendental-free, tie-free ``pv_fn`` for known-answer
     tests.  The policy over the S*S cells is a board-dependent
     affine permutation of distinct integer weights divided by their (exact) integer
     sum -- a single correctly-rounded float32 division per cell, so it is bit-portable
-    across numpy builds -- and the value is an integer in [-1000, 1000] / 1000."""
+    across numpy builds -- and the value is an integer in [-1000, 1000] / 1000
+    (``zero_value``: always 0, so q stays 0 and selection depends on the priors and the
+    exploration noise only).  Vectorised over the batch (integer arithmetic: the values
+    do not depend on the batch size)."""
     C = size * size
     P = 127 if C <= 127 else 227 if C <= 227 else 401   # a prime >= C
     assert C <= P
+    idx = np.arange(C, dtype=np.int64)
 
     def fn(x):
         x = np.asarray(x)
         B = x.shape[0]
-        prob = np.empty((B, C), np.float32)
-        val = np.empty((B,), np.float32)
-        idx = np.arange(C, dtype=np.int64)
-        for b in range(B):
-            planes = (x[b].reshape(3, C) > 0.5).astype(np.int64)
-            h = np.int64(1469598103 + salt)
-            code = planes[0] * 1 + planes[1] * 2 + planes[2] * 4
-            for c in range(C):
-                h = (h * 1000003 + code[c] * 7919 + c) % 2147483647
-            h = int(h)
-            a = 1 + h % (P - 1)
-            off = (h // 131) % P
-            wts = 1 + ((a * idx + off) % P) * 3 + (idx % 3)     # pairwise distinct
-            tot = int(wts.sum())
-            prob[b] = wts.astype(np.float32) / np.float32(tot)
-            val[b] = np.float32((h // 7) % 2001 - 1000) / np.float32(1000)
-        return prob, val
+        planes = (x.reshape(B, 3, C) > 0.5).astype(np.int64)
+        code = planes[:, 0] * 1 + planes[:, 1] * 2 + planes[:, 2] * 4        # [B, C]
+        h = np.full(B, 1469598103 + salt, np.int64)
+        for c in range(C):
+            h = (h * 1000003 + code[:, c] * 7919 + c) % 2147483647
+        a = 1 + h % (P - 1)
+        off = (h // 131) % P
+        wts = 1 + ((a[:, None] * idx[None, :] + off[:, None]) % P) * 3 + (idx % 3)[None, :]   # pairwise distinct
+        tot = wts.sum(1)
+        prob = wts.astype(np.float32) / tot.astype(np.float32)[:, None]
+        val = ((h // 7) % 2001 - 1000).astype(np.float32) / np.float32(1000)
+        if zero_value:
+            val = np.zeros(B, np.float32)
+        return prob.astype(np.float32), val.astype(np.float32)
 
     return fn

@@ -33,3 +33,24 @@ def test_round_trip_other_shapes(tmp_path):
     for k in w:
         assert back[k].shape == w[k].shape and (back[k] == w[k]).all(), k
     assert ckpt.crc32c(b"123456789") == 0xE3069283          # the CRC-32C check value
+
+
+def test_reader_skips_non_float_entries_and_writes_atomically(tmp_path):
+    """A checkpoint that also holds an int64 global_step (tf.train.Saver saves every variable): the float
+    tensors load, the rest is skipped with a warning (the reference's load_pretrained skips what it cannot
+    use, network.py:136-160); no temporary files are left; the marker keeps the history of prefixes."""
+    import os
+    import warnings
+    from alphafive_b200 import ckpt
+    w = {"bone/conv1/kernel": np.arange(12, dtype=np.float32).reshape(1, 2, 3, 2), "bone/conv1/bias": np.ones(2, np.float32),
+         "global_step": np.array(6960, np.int64)}
+    for step in (10, 20):
+        ckpt.write_bundle(str(tmp_path / f"alphaFive-{step}"), w)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        got = ckpt.read_bundle(str(tmp_path))
+    assert sorted(got) == ["bone/conv1/bias", "bone/conv1/kernel"] and (got["bone/conv1/kernel"] == w["bone/conv1/kernel"]).all()
+    assert any("global_step" in str(r.message) for r in rec)
+    assert not [f for f in os.listdir(tmp_path) if ".tmp" in f]
+    marker = open(tmp_path / "checkpoint").read()
+    assert marker.startswith('model_checkpoint_path: "alphaFive-20"') and '"alphaFive-10"' in marker

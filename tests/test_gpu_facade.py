@@ -131,3 +131,76 @@ def test_driver_loops(cuda_lib):
     assert w0 + w1 <= N and used == N
     assert out["moves"] == int(out["plies"].sum())
     arena.close()
+
+
+def test_player_tree_view_pruning_and_reset(cuda_lib):
+    """Player.tree (player.py:29) as a mapping of State objects, equal to the oracle's table; the device GC
+    leaves no key the reference's pruning_tree (player.py:149-164) would delete; reset(search_tree=...)."""
+    from alphafive_b200.genData.player import Player, state_to_board, board_to_state
+    S = 11
+    cfg = _cfg(simulation_per_step=90, upper_simulation_per_step=120)
+    pv = omcts.table_pv_fn(S, 5)
+    pl = Player(cfg, training=False, pv_fn=pv)
+    ocfg = omcts.SearchConfig(simulation_per_step=90, upper_simulation_per_step=120)
+    opl = omcts.OraclePlayer(ocfg, training=False, pv_fn=pv)
+    assert len(pl.tree) == 0
+    state, last = pl.get_init_state(), None
+    for ply in range(4):
+        board = state_to_board(state, S)
+        _, action = pl.get_action(state, last_action=last)
+        _, oaction = opl.get_action(board, last)
+        assert action == oaction
+        tree = pl.tree
+        # every key the oracle's (never pruned) table holds *and* that contains the root's stones is there,
+        # with the same sum_n; nothing else is
+        root_own, root_opp = board == 1, board == -1
+        want = {}
+        for key, node in opl.table.items():
+            b = np.frombuffer(key, np.int8).reshape(S, S)
+            q = int((b != 0).sum()) - int((board != 0).sum())
+            own, opp = (b == 1, b == -1) if q % 2 == 0 else (b == -1, b == 1)
+            if q >= 0 and (own >= root_own).all() and (opp >= root_opp).all():
+                want[board_to_state(b)] = node.sum_n
+        assert {k: v.sum_n for k, v in tree.items()} == want
+        # reference pruning predicate relative to the current root: nothing left to delete
+        for key in tree:
+            b = state_to_board(key, S)
+            deletable = key != state and (root_own >= (b == 1)).all() and (root_opp >= (b == -1)).all()
+            assert not deletable, key
+        assert pl.pruning_tree(board, state) is None and len(pl.tree) == len(want)
+        # a node as the reference exposes it
+        node = tree[state]
+        n, w, p, sum_n = opl.root_stats(board)
+        assert node.sum_n == sum_n and set(node.a) == set(orules.legal_actions(board))
+        for (i, j), e in node.a.items():
+            c = i * S + j
+            assert e.n == n[c] and e.w == w[c] and e.p == p[c] and (e.q == w[c] / n[c] if n[c] else e.q == 0)
+        with pytest.raises(KeyError):
+            tree["x" + state]
+        nxt = orules.play(board, action)
+        state, last = board_to_state(nxt), action
+    with pytest.raises(NotImplementedError):
+        pl.reset(search_tree={})
+    pl.reset(None)
+    assert len(pl.tree) == 0 and pl.root_state is None
+    pl.close()
+
+
+def test_player_engine_follows_budget_growth(cuda_lib):
+    """config.simulation_per_step is read lazily and may grow (choose_best_player.py:25): the table is
+    re-sized instead of silently dropping expansions."""
+    from alphafive_b200.genData.player import Player
+    cfg = _cfg(simulation_per_step=20, upper_simulation_per_step=30)
+    pv = omcts.table_pv_fn(11, 2)
+    pl = Player(cfg, training=False, pv_fn=pv)
+    s0 = pl.get_init_state()
+    pl.get_action(s0)
+    cap0 = pl._engine.cfg.node_capacity
+    cfg.simulation_per_step, cfg.upper_simulation_per_step = 3000, 3100
+    _, action = pl.get_action(s0)
+    assert pl._engine.cfg.node_capacity > cap0
+    opl = omcts.OraclePlayer(omcts.SearchConfig(simulation_per_step=3000, upper_simulation_per_step=3100),
+                             training=False, pv_fn=pv)
+    assert opl.get_action(np.zeros((11, 11), np.int8), None)[1] == action
+    assert pl.tree[s0].sum_n == 3000
+    pl.close()

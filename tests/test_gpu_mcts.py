@@ -75,9 +75,10 @@ def test_deterministic_game_with_tree_reuse(cuda_lib, S):
 
 
 def test_matches_oracle_on_many_roots_with_device_net(cuda_lib):
-    """N different mid-game roots searched in lock-step with the on-device fp32 net; the
-    oracle runs the same searches with the oracle net.  Visit counts agree exactly on
-    nearly every root (fp32 rounding of the two nets can flip a near-tie)."""
+    """N different mid-game roots searched in lock-step with the on-device net.  (i) The oracle search driven
+    by the *same* device net (DeviceNet.eval as its pv_fn) must give identical visit counts on every root:
+    the tree pass itself is exact.  (ii) With the fp32 oracle net instead, a root may differ only because the
+    two nets round differently (<= 1e-4, tested in test_gpu_net.py) and flip a near-tie; that is rare."""
     from alphafive_b200.net import DeviceNet, glorot_init
     from oracle import net as onet
     S, sims = 11, 64
@@ -92,10 +93,14 @@ def test_matches_oracle_on_many_roots_with_device_net(cuda_lib):
     onet_ = onet.OracleNet(S, w)
     same = 0
     for j in range(48):
-        pl = omcts.OraclePlayer(omcts.SearchConfig(simulation_per_step=sims, upper_simulation_per_step=sims + 100),
-                                training=False, pv_fn=onet_.eval)
         la = tuple(int(v) for v in last[j])
-        pl.get_action(boards[j], la if la[0] >= 0 else None)
+        la = la if la[0] >= 0 else None
+        cfg = omcts.SearchConfig(simulation_per_step=sims, upper_simulation_per_step=sims + 100)
+        pl = omcts.OraclePlayer(cfg, training=False, pv_fn=net.eval)
+        pl.get_action(boards[j], la)
+        assert (pl.root_stats(boards[j])[0] == n[j]).all(), j
+        pl = omcts.OraclePlayer(cfg, training=False, pv_fn=onet_.eval)
+        pl.get_action(boards[j], la)
         same += int((pl.root_stats(boards[j])[0] == n[j]).all())
         assert n[j].sum() == sims - 1
     assert same >= 44, same
@@ -191,4 +196,43 @@ def test_self_play_records(cuda_lib):
             assert plies[0]["result"] == (1 if L % 2 == 1 else -1)
         np.testing.assert_allclose([r["weight"] for r in plies], orules.ply_weights(L, 0.94), atol=1e-6)
     assert np.mean(lens) > 12
+    eng.close()
+
+
+def test_record_arena_overflow_is_loud_and_never_splits_a_game(cuda_lib):
+    """A record arena that is too small: harvest raises (A5_ERR_CAPACITY), counters()['records_dropped'] counts
+    the lost plies, and what *is* returned are whole games with contiguous plies (emit_game reserves a
+    game's plies atomically -- no roll-back that could hand two warps overlapping ranges)."""
+    from alphafive_b200._lib import A5Error
+    from alphafive_b200.engine import parse_records
+    from alphafive_b200.net import DeviceNet
+    S, N, sims = 11, 256, 8
+    net = DeviceNet(S, N)
+    eng = _engine(S, N, sims, sims + 4, training=True, auto_play=True, seed=2, record_capacity=400)
+    prob = torch.empty((N, S * S), device="cuda")
+    value = torch.empty((N,), device="cuda")
+    eng.step()
+    raised = False
+    for it in range(4000):
+        net.forward_raw(eng.planes_ptr, N, prob, value)
+        eng.step(prob, value)
+    buf = torch.zeros((400, eng.record_stride), dtype=torch.uint8, device="cuda")
+    try:
+        eng.harvest(buf)
+    except A5Error as err:
+        raised = "records lost" in str(err)
+    assert raised
+    torch.cuda.synchronize()
+    recs = parse_records(buf, S)                      # the arena content that was copied before the error
+    i = 0
+    games = 0
+    while i < len(recs) and recs[i]["game_len"] > 0 and i + recs[i]["game_len"] <= 400:
+        L = recs[i]["game_len"]
+        gid = (recs[i]["game_id"], recs[i]["game_serial"])
+        assert [r["ply"] for r in recs[i:i + L]] == list(range(L))
+        assert all((r["game_id"], r["game_serial"]) == gid for r in recs[i:i + L])
+        i += L
+        games += 1
+    assert games >= 3 and i > 400 - 121
+    assert eng.counters()["records_dropped"] > 0
     eng.close()
