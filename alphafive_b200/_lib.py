@@ -66,6 +66,7 @@ _SIGS = {
     "a5_engine_root_stats": (_I, [_P, _P, _P, _P, _P, _P]),
     "a5_engine_node_stats": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "a5_engine_tau": (_P, [_P]),
+    "a5_engine_get_roots": (_I, [_P, _P, _P, _P]),
     "a5_dirichlet_sample": (_I, [C.c_uint64, C.c_float, _I, _I, _P, _P]),
     "a5_engine_table_dump": (_I, [_P, _I, _P, _P, _I, C.POINTER(C.c_int32), _P]),
     "a5_record_stride": (_I, [_I]),

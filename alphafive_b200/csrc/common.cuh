@@ -30,6 +30,32 @@ void set_error(const char* fmt, ...);
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
+// In-situ kernel timing (a5__debug_ktime_*): every kernel of a self-play pass can stamp %globaltimer when
+// its first thread starts and when each CTA has finished, into its slot of a device buffer
+// [slot][32 sub-slots][start_min, end_max]; a fold kernel at the end of the pass turns the stamps into
+// per-slot sums "end of my predecessor -> my end" (these partition the pass exactly, whatever the overlap
+// between programmatic-dependent launches) and "my first start -> my end".  Works inside CUDA-graph
+// replays; costs one predicated branch per CTA when off (kt == nullptr).
+// ---------------------------------------------------------------------------
+constexpr int KT_SLOTS = 16;
+constexpr int KT_SUB = 32;
+enum { KT_C1BITS = 0, KT_CONV1 = 1, KT_CONV0 = 2 /* .. +7: the 8 block-conv launches */, KT_HEADS = 10, KT_STEP = 11, KT_FOLD = 12 };
+unsigned long long* kt_slot(int slot);          // device pointer of a slot, or nullptr while timing is off (net_tc.cu)
+
+__device__ __forceinline__ unsigned long long kt_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void kt_begin(unsigned long long* kt) {
+  if (kt && threadIdx.x == 0) atomicMin(kt + 2 * (blockIdx.x & (KT_SUB - 1)), kt_now());
+}
+// call after a CTA-wide barrier that follows the CTA's last work
+__device__ __forceinline__ void kt_end(unsigned long long* kt) {
+  if (kt && threadIdx.x == 0) atomicMax(kt + 2 * (blockIdx.x & (KT_SUB - 1)) + 1, kt_now());
+}
+
+// ---------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011).  Key = (seed, game),
 // counter = (event counter lo/hi, lane-specific a, b): any draw is addressable,
 // so results do not depend on scheduling or on the number of ranks.

@@ -47,6 +47,7 @@ struct EP {
   uint8_t* out_rec; int32_t* out_count;
   long long* gstat;
   int8_t* planes;
+  unsigned long long* kt;       // tooling: in-situ kernel timing slot (common.cuh), or null
 };
 
 // --------------------------------------------------------------------------- //
@@ -649,11 +650,8 @@ struct Warp {
 #define A5_STEP_MINB (NCH <= 4 ? 7 : 4)
 #endif
 template <int NCH>
-__global__ void __launch_bounds__(WPB * 32, A5_STEP_MINB) k_step(const __grid_constant__ EP P, const float* __restrict__ prob,
-                                                  const float* __restrict__ value) {
-  __shared__ __align__(16) int8_t s_board[WPB][256];
-  __shared__ __align__(16) float s_f[WPB][256];
-  __shared__ uint32_t s_valid[WPB][4 * NCH];
+__device__ __forceinline__ void step_body(const EP& P, const float* __restrict__ prob, const float* __restrict__ value,
+                                          int8_t (*s_board)[256], float (*s_f)[256], uint32_t (*s_valid)[4 * NCH]) {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * WPB + wid;
   if (g >= P.N) return;
@@ -788,6 +786,17 @@ __global__ void __launch_bounds__(WPB * 32, A5_STEP_MINB) k_step(const __grid_co
     if (g_step_dbg_on && g < 8192) { g_step_dbg[g] = step_now() - dbg_t0; g_step_dbg[8192 + g] = dbg_flags; }
   }
   W.flush();
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(WPB * 32, A5_STEP_MINB) k_step(const __grid_constant__ EP P, const float* __restrict__ prob,
+                                                  const float* __restrict__ value) {
+  __shared__ __align__(16) int8_t s_board[WPB][256];
+  __shared__ __align__(16) float s_f[WPB][256];
+  __shared__ uint32_t s_valid[WPB][4 * NCH];
+  kt_begin(P.kt);
+  step_body<NCH>(P, prob, value, s_board, s_f, s_valid);
+  if (P.kt) { __syncthreads(); kt_end(P.kt); }
 }
 
 template <int NCH>
@@ -1120,6 +1129,7 @@ int a5_engine_set_roots(a5_engine* e, const int8_t* d_boards, const int32_t* d_l
 
 int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void* stream) {
   A5_ARG(e && ((d_prob == nullptr) == (d_value == nullptr)));
+  e->p.kt = kt_slot(KT_STEP);
   DISPATCH(k_step, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_prob, d_value);
   return A5_OK;
 }
@@ -1175,6 +1185,14 @@ int a5_engine_node_stats(a5_engine* e, const int8_t* d_boards, int32_t* d_n, flo
 }
 
 double* a5_engine_tau(a5_engine* e) { return e ? e->p.tau : nullptr; }
+
+int a5_engine_get_roots(a5_engine* e, int8_t* d_boards, int32_t* d_last, void* stream) {
+  A5_ARG(e && d_boards);
+  cudaStream_t st = (cudaStream_t)stream;
+  A5_CUDA(cudaMemcpy2DAsync(d_boards, e->p.C, e->p.root_board, e->p.KB, e->p.C, e->p.N, cudaMemcpyDeviceToDevice, st));
+  if (d_last) A5_CUDA(cudaMemcpyAsync(d_last, e->p.root_last, sizeof(int32_t) * e->p.N, cudaMemcpyDeviceToDevice, st));
+  return A5_OK;
+}
 
 int a5_dirichlet_sample(uint64_t seed, float alpha, int n_legal, int n_draws, float* d_eta, void* stream) {
   A5_ARG(d_eta && n_legal > 0 && n_legal <= 256 && n_draws > 0 && alpha > 0.0f);

@@ -27,6 +27,7 @@ struct FCHead {
   int N;                 // padded outputs (multiple of 16, <= 256)
   int C;                 // real outputs (policy) / 64 (value)
   int fold;              // hi*[Whi|Wlo] as one N = 2N MMA (2N <= 256)
+  unsigned long long* kt; // tooling: in-situ kernel timing slot (common.cuh), or null
 };
 
 struct FCBarriers {
@@ -37,6 +38,7 @@ struct FCBarriers {
 __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__ FCHead P, const __grid_constant__ FCHead V,
                                                          int mtiles, int n) {
   extern __shared__ __align__(128) uint8_t smem[];
+  kt_begin(P.kt);
   const bool is_value = (int)blockIdx.x >= mtiles;
   const FCHead& H = is_value ? V : P;
   const int mt = is_value ? blockIdx.x - mtiles : blockIdx.x;
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  kt_end(P.kt);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
@@ -262,6 +265,7 @@ int heads_forward(a5_net* net, HeadsState* h, int n, float* prob, float* value, 
   P.nst = h->nst_pol; P.N = h->n_pol; P.C = net->C; P.fold = 2 * h->n_pol <= 256;
   V.A = h->a_val; V.W = h->w_val; V.bias = net->vfc1_b; V.w2 = net->vfc2_w; V.b2 = net->vfc2_b; V.out = value;
   V.nst = h->nst_val; V.N = 64; V.C = 64; V.fold = 1;
+  P.kt = kt_slot(KT_HEADS);
   const int mtiles = (n + 127) / 128;
   k_tc_fc<<<2 * mtiles, FC_THREADS, h->smem, st>>>(P, V, mtiles, n);
   A5_CUDA(cudaGetLastError());

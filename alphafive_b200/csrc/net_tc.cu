@@ -55,6 +55,7 @@ struct TCLayer {
                                  // 150-450 MB activation tensor are then still in the 126 MB L2
   int nslab_buf, w_bytes;        // pair kernel: A slab buffers, bytes of the weight region (ring or resident set)
   unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
+  unsigned long long* kt;        // tooling: in-situ kernel timing slot (common.cuh), or null
   // fused 1x1 head conv + ELU in the epilogue (network.py:69-70 value, :81-82 policy): the
   // layer's own activation is then not stored; the head output goes out as the A operand of
   // the dense layer that follows (k_tc_fc), K ordered (cell, channel).
@@ -448,6 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   const int g_first = 2 * (int)(blockIdx.x >> 1) + (int)rank, g_end = 2 * npairs, g_step = (int)gridDim.x;
 
   pdl_launch_dependents();
+  kt_begin(L.kt);
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (L.head_ch) {
     for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC2_THREADS) s_hw[i] = L.head_w[i];
@@ -687,6 +689,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                      // nobody leaves while the peer may still touch its barriers / smem
+  kt_end(L.kt);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -789,8 +792,11 @@ struct __align__(8) C1MBarriers {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // int8 planes [n][3][C] -> bitboards [n][plane 3][8 words]: one warp per board.
-__global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ planes, int n, int C, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ planes, int n, int C, uint32_t* __restrict__ bits,
+                                                 unsigned long long* kt) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  kt_begin(kt);
+  if (kt && b >= n) { __syncthreads(); return; }           // (timing on: everybody meets at the barrier below)
   if (b >= n) return;
   const int8_t* p = planes + (size_t)b * 3 * C;
   uint32_t mine = 0;
@@ -803,13 +809,15 @@ __global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ plan
       if (lane == pl * 8 + k) mine = m;
     }
   if (lane < C1M_BW) bits[(size_t)b * C1M_BW + lane] = mine;
+  if (kt) { __syncthreads(); kt_end(kt); }
 }
 
 __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __restrict__ bits, const __half* __restrict__ wpk,
                                                           const float* __restrict__ bias, __half* __restrict__ out,
                                                           long long plane_rows, int S, int pitch, int per_board, int guard,
-                                                          int n, int ntiles) {
+                                                          int n, int ntiles, unsigned long long* kt) {
   extern __shared__ __align__(128) uint8_t smem[];
+  kt_begin(kt);
   uint8_t* a_buf = smem;                                       // 2 A tiles [kchunk 10][row 128][8]
   uint8_t* w_buf = smem + C1M_NA * C1M_ATILE;                  // [kchunk 16][hi 32 | lo 32][8]
   uint4* s_lut = (uint4*)(w_buf + C1M_WBYTES);                 // window pattern -> 8 halves (5 used)
@@ -972,6 +980,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
   }
   tc_fence_before();
   __syncthreads();
+  kt_end(kt);
   if (warp == C1M_BUILD_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
@@ -1002,6 +1011,40 @@ __global__ void k_tc_unpack(const __half* __restrict__ x, int ch, long long plan
   out[i] = (hi + lo) * (1.0f / ACT_SCALE);
 }
 
+}  // namespace a5
+
+// ------------------------------------------------------------------ in-situ kernel timing (common.cuh)
+namespace a5 {
+static unsigned long long* g_kt_dev = nullptr;       // [KT_SLOTS][KT_SUB][2] stamps + [KT_SLOTS][3] sums + [1] previous pass end
+static bool g_kt_on = false;
+unsigned long long* kt_slot(int slot) { return (g_kt_on && g_kt_dev) ? g_kt_dev + (size_t)slot * KT_SUB * 2 : nullptr; }
+
+// one warp: fold the stamps of the pass that just ended into the sums, reset the stamps
+__global__ void k_kt_fold(unsigned long long* kt) {
+  unsigned long long* acc = kt + (size_t)KT_SLOTS * KT_SUB * 2;
+  unsigned long long* prev_end = acc + KT_SLOTS * 3;
+  const int lane = threadIdx.x;
+  unsigned long long prev = *prev_end;
+  for (int s = 0; s < KT_SLOTS; ++s) {
+    unsigned long long* p = kt + (size_t)s * KT_SUB * 2 + 2 * lane;
+    unsigned long long st = p[0], en = p[1];
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, st, o), b = __shfl_xor_sync(0xffffffffu, en, o);
+      st = a < st ? a : st;
+      en = b > en ? b : en;
+    }
+    p[0] = ~0ull; p[1] = 0ull;
+    if (s == KT_FOLD) { en = kt_now(); st = prev; }          // the fold itself closes the pass
+    if (en == 0ull) continue;                                // slot not used in this pass
+    if (lane == 0 && prev != 0ull) {
+      acc[s * 3 + 0] += en > prev ? en - prev : 0ull;       // predecessor's end -> my end
+      acc[s * 3 + 1] += en - st;                            // my first start -> my end
+      acc[s * 3 + 2] += 1ull;
+    }
+    prev = en > prev ? en : prev;
+  }
+  if (lane == 0) *prev_end = prev;
+}
 }  // namespace a5
 
 // ------------------------------------------------------------------ host side
@@ -1171,10 +1214,10 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   if (parts & A5_NET_PART_FRONT) {
     const int ntiles = (int)((nrows1 + 127) / 128);
     const int grid1 = ntiles < C1M_CTAS * tc->front_sms ? ntiles : C1M_CTAS * tc->front_sms;
-    k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits);
+    k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits, kt_slot(KT_C1BITS));
     A5_CUDA(cudaGetLastError());
     k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
-                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles);
+                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles, kt_slot(KT_CONV1));
   }
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
@@ -1216,6 +1259,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     // conv1 writes ascending; from there on every layer starts where its inputs were touched last
     L.reverse = tc->zigzag && (nexec++ % 2 == 0);
     L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
+    L.kt = kt_slot(KT_CONV0 + (nexec - 1));
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
     {
@@ -1275,6 +1319,41 @@ int a5_net_forward_parts(a5_net* net, const int8_t* d_planes, int n, float* d_pr
   if (!net->has_weights) { set_error("a5_net_forward_parts: no weights set"); return A5_ERR_STATE; }
   if (n == 0 || parts == 0) return A5_OK;
   return tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream, parts);
+}
+
+// internal tooling (not part of alphafive.h): in-situ kernel timing.  enable(1) arms the stamps for kernels
+// launched (or captured into a graph) from now on and clears the sums; fold(stream) closes a pass (launch it
+// after the tree pass, also inside the captured graph); read copies double[KT_SLOTS][3] =
+// {ns predecessor-end -> end, ns start -> end, passes}.
+int a5__debug_ktime_enable(int on) {
+  const size_t bytes = ((size_t)KT_SLOTS * KT_SUB * 2 + KT_SLOTS * 3 + 1) * sizeof(unsigned long long);
+  if (on && !g_kt_dev) A5_CUDA(cudaMalloc(&g_kt_dev, bytes));
+  if (on) {
+    A5_CUDA(cudaDeviceSynchronize());
+    A5_CUDA(cudaMemset(g_kt_dev, 0, bytes));
+    k_kt_fold<<<1, 32>>>(g_kt_dev);                      // sets every stamp to (start_min = ~0, end_max = 0)
+    A5_CUDA(cudaGetLastError());
+    A5_CUDA(cudaDeviceSynchronize());
+    // sums and "previous pass end" cleared: the first pass after this only sets the reference point
+    A5_CUDA(cudaMemset(g_kt_dev + (size_t)KT_SLOTS * KT_SUB * 2, 0, (KT_SLOTS * 3 + 1) * sizeof(unsigned long long)));
+    A5_CUDA(cudaDeviceSynchronize());
+  }
+  g_kt_on = on != 0;
+  return A5_OK;
+}
+int a5__debug_ktime_fold(void* stream) {
+  if (!g_kt_on || !g_kt_dev) return A5_OK;
+  k_kt_fold<<<1, 32, 0, (cudaStream_t)stream>>>(g_kt_dev);
+  A5_CUDA(cudaGetLastError());
+  return A5_OK;
+}
+int a5__debug_ktime_read(double* h_out) {
+  A5_ARG(h_out && g_kt_dev);
+  unsigned long long acc[KT_SLOTS * 3];
+  A5_CUDA(cudaDeviceSynchronize());
+  A5_CUDA(cudaMemcpy(acc, g_kt_dev + (size_t)KT_SLOTS * KT_SUB * 2, sizeof(acc), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < KT_SLOTS * 3; ++i) h_out[i] = (double)acc[i];
+  return A5_OK;
 }
 
 // internal tooling: also store the block3 / block5 activations (normally consumed in-register by

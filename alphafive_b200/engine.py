@@ -125,6 +125,13 @@ class SearchEngine:
         check(self.lib.a5_engine_node_stats(self.handle, ptr(boards), ptr(n), ptr(w), ptr(p), ptr(s), stream_ptr()))
         return n, w, p, s
 
+    def roots(self):
+        """(boards int8[N,S,S], last int32[N]) -- where every game stands (copies)."""
+        boards = torch.empty((self.N, self.S, self.S), dtype=torch.int8, device=self.device)
+        last = torch.empty((self.N,), dtype=torch.int32, device=self.device)
+        check(self.lib.a5_engine_get_roots(self.handle, ptr(boards), ptr(last), stream_ptr()))
+        return boards, last
+
     def tau(self) -> torch.Tensor:
         """Zero-copy float64 [N] view of every game's temperature (Player.tau)."""
         return _view(self.lib.a5_engine_tau(self.handle), (self.N,), torch.float64, self.device)

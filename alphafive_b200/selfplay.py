@@ -81,9 +81,45 @@ class SelfPlay:
                 self._pass()
         self.passes += k
 
-    def harvest(self):
+    def harvest(self, buf=None):
         """(records uint8 [count, stride] on the device, games finished since last call)."""
-        return self.engine.harvest(self.record_buf)
+        return self.engine.harvest(self.record_buf if buf is None else buf)
+
+    def kernel_accounting(self, passes=200):
+        """In-situ time of every kernel of a pass, measured inside CUDA-graph replays of the running workload
+        (%globaltimer stamps, a5__debug_ktime_*): dict name -> (us from the predecessor's end to this
+        kernel's end, us from its first CTA's start to its end); the first values partition the pass exactly.
+        The games advance by ``passes + 1`` passes."""
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, stream_ptr
+        lib = _lib.load()
+        for name in ("a5__debug_ktime_enable", "a5__debug_ktime_fold", "a5__debug_ktime_read"):
+            getattr(lib, name).restype = C.c_int
+        lib.a5__debug_ktime_fold.argtypes = [C.c_void_p]
+        lib.a5__debug_ktime_read.argtypes = [C.POINTER(C.c_double)]
+        self.start()
+        torch.cuda.synchronize()
+        check(lib.a5__debug_ktime_enable(1))
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._pass()
+                check(lib.a5__debug_ktime_fold(stream_ptr()))
+            for _ in range(passes + 1):            # the first replay only sets the reference point
+                g.replay()
+            out = (C.c_double * 48)()
+            check(lib.a5__debug_ktime_read(out))
+        finally:
+            check(lib.a5__debug_ktime_enable(0))
+        self.passes += passes + 1
+        names = ["k_c1_bits", "k_tc_conv1m"] + [f"k_tc_conv2[{i}]" for i in range(8)] + ["k_tc_fc", "k_step", "(fold)"]
+        table = {}
+        for i, nm in enumerate(names):
+            cnt = out[3 * i + 2]
+            if cnt > 0:
+                table[nm] = (out[3 * i] / cnt / 1000.0, out[3 * i + 1] / cnt / 1000.0)
+        return table
 
     def harvest_games(self):
         """Finished games as the reference's replay tuples (player.py:77-82):

@@ -5,11 +5,16 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
 
 A *step* is `sims` lock-step passes (network forward over all N pending leaves + one tree
-kernel pass) over the N concurrent games of this rank: on average one move per game.
+kernel pass) over the N concurrent games of this rank -- on average one move per game -- followed by
+the harvest of the finished games, the all-gather of their records over NCCL (N > 1, side stream,
+overlapped with the next step's passes) and their push into the device-resident RandomStack (the sink of
+main.py:60-64) on every rank.
 `value` is whole-job moves/s with everything resident in HBM (games are played, recorded
 and restarted on the device); `e2e` is the same metric through the host-buffer API
 (BatchedPlayer.get_actions: H2D boards, search, D2H policies/actions/next boards each
-move).  One JSON line on stdout (rank 0).
+move) over --steps consecutive moves of a steady-state mix of positions.  The other BASELINE
+configurations (15x15 / 800 sims, the arena, a single game) are reported under `configs`.
+One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -25,13 +30,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_LEAF = {11: 118_727_264, 15: 221_522_528}     # 2*MAC, biases/activations excluded
+CONV_MAC_PER_CELL = 485_376          # the ten 3x3(+1x1) block convs, MACs per board cell (58,730,496 @ 11x11)
 METRIC = "self-play moves/sec at 11x11, 500 sims/move; NN leaf-evals/sec"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
@@ -39,17 +45,16 @@ def parse():
     ap.add_argument("--sims", type=int, default=500)
     ap.add_argument("--upper", type=int, default=None)
     ap.add_argument("--net-mode", default=os.environ.get("A5_NET_MODE", "auto"), choices=["auto", "fp32", "tc"])
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=None,
+                    help="timed get_actions calls of the end-to-end leg (default: max(--steps, 8); 0 disables it)")
     ap.add_argument("--preroll-moves", type=int, default=48,
                     help="untimed moves at --preroll-sims before the warm-up, so games are spread over all plies")
     ap.add_argument("--preroll-sims", type=int, default=40)
+    ap.add_argument("--buffer", type=int, default=12000, help="RandomStack length in plies (config.buffer_size)")
+    ap.add_argument("--accounting-passes", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg4 / cfg5 / cfg1 legs")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="two half batches pipelined on SM-partitioned streams (CUDA green contexts) instead of the "
-                         "single-stream CUDA-graph replay; bit-identical results, measured no faster on a power-capped "
-                         "B200 (DESIGN.md section 8)")
-    ap.add_argument("--small-sms", type=int, default=16, help="SMs of the small partition of the pipeline")
     return ap.parse_args()
 
 
@@ -88,14 +93,19 @@ class ClockSampler:
         self.proc.terminate()
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 # --------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference loop, all host cores
+# CPU arm: the oracle port of the reference loop on the host cores.  Two topologies:
+#   * "port": one independent process per core (numpy MCTS + torch-CPU fp32 net in-process, pv_fn mode)
+#   * "pipe": the reference's own topology (main.py:50-55, networkAPI.py:43-78): a parent thread batches the
+#     leaf requests of `workers` child processes over multiprocessing Pipes and evaluates them with one net
+# profiles/r02_cpu_calibration.json relates both to the UNMODIFIED reference Player timed in the build container.
 # --------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """Plays `moves` self-play moves (sims simulations each, training mode) with the oracle
@@ -133,6 +143,87 @@ def cpu_moves_per_sec(S, sims, upper, workers, moves_each, seed0=0):
     return moves / busy, evals / busy, wall
 
 
+def _pipe_worker(pipe, q, S, sims, upper, moves, seed):
+    """main.gen_data's role (main.py:82-94) with the oracle Player: every leaf goes to the parent over the
+    Pipe (player.py:194-197: send [x], spin on poll, recv()[0])."""
+    import numpy as np
+    from oracle import mcts, rules
+
+    def pv(x):
+        pipe.send([x[0]])
+        while not pipe.poll():
+            pass
+        p, v = pipe.recv()[0]
+        return p[None], np.float32([v])
+
+    cfg = mcts.SearchConfig(board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
+    pl = mcts.OraclePlayer(cfg, training=True, pv_fn=pv, rng=np.random.default_rng(seed))
+    board, last = np.zeros((S, S), np.int8), None
+    q.put("ready")
+    t0 = time.perf_counter()
+    for _ in range(moves):
+        _, action = pl.get_action(board, last)
+        board, last = rules.play(board, action), action
+    q.put((moves, pl.stat_leaf_evals, time.perf_counter() - t0))
+
+
+def cpu_pipe_topology(S, sims, upper, workers, moves_each, net_threads, seed0=0):
+    """The reference's process topology: `workers` processes + one inference thread in the parent
+    (networkAPI.py:43-78: wait 1 ms, drain ready pipes, one batched eval, reply per pipe)."""
+    import multiprocessing as mp
+    from multiprocessing import connection
+    import numpy as np
+    import torch
+    from oracle import net as onet
+    torch.set_num_threads(max(1, net_threads))
+    model = onet.OracleNet(S, onet.glorot_weights(S, 0))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pipes, procs = [], []
+    for i in range(workers):
+        me, you = ctx.Pipe()
+        pipes.append(me)
+        p = ctx.Process(target=_pipe_worker, args=(you, q, S, sims, upper, moves_each, seed0 + i), daemon=True)
+        p.start()
+        procs.append(p)
+    done = [False]
+
+    def serve():
+        while not done[0]:
+            ready = connection.wait(pipes, timeout=0.001)
+            if not ready:
+                continue
+            data, owners = [], []
+            for pp in ready:
+                try:
+                    while pp.poll():
+                        msg = pp.recv()
+                        data.extend(msg)
+                        owners.append((pp, len(msg)))
+                except (EOFError, OSError):
+                    if pp in pipes:
+                        pipes.remove(pp)
+            if not data:
+                continue
+            prob, value = model.eval(np.asarray(data, np.float32))
+            k = 0
+            for pp, n in owners:
+                pp.send([(prob[k + j], float(value[k + j])) for j in range(n)])
+                k += n
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    for _ in range(workers):
+        assert q.get() == "ready"
+    t0 = time.perf_counter()
+    res = [q.get() for _ in range(workers)]
+    wall = time.perf_counter() - t0
+    done[0] = True
+    for p in procs:
+        p.join(timeout=5)
+    return sum(r[0] for r in res) / wall, sum(r[1] for r in res) / wall, wall
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,15 +242,26 @@ def run_reference(a):
         tot_e += e
     wall = time.perf_counter() - t0
     v = tot_m / a.steps
-    sample = f"{workers} processes x 1 move of {sims} sims per step from the empty board, training mode, oracle port + torch-CPU fp32 net (1 thread each)"
+    sample = (f"{workers} processes x 1 move of {sims} sims per step from the empty board, training mode, oracle port + "
+              f"torch-CPU fp32 net (1 thread each); host has {cores} cores")
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "moves/s", "leaf_evals_per_s": tot_e / a.steps,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * wall / max(1, a.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, max(1, a.gpus)), "board": S, "sims": sims, "upper_sims": upper},
-        "cpu_baseline": {"value": v, "unit": "moves/s", "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "moves/s", "cores": workers, "host_cores": cores, "kind": "port", "sample": sample,
+                         "calibration": calibration_note()},
         "e2e": {"value": v, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def calibration_note():
+    p = os.path.join(ROOT, "profiles", "r02_cpu_calibration.json")
+    try:
+        d = json.load(open(p))
+        return {k: d[k] for k in ("port_over_reference_single", "port_over_reference_pipe5", "where") if k in d}
+    except Exception:
+        return None
 
 
 def workload_name(a, world):
@@ -168,7 +270,59 @@ def workload_name(a, world):
 
 
 # --------------------------------------------------------------------------------------
+def conv_roofline(kt, S, N, pk, traffic):
+    """Dominant kernel = k_tc_conv2 (eight launches per pass: block3/block4 conv1 run as one layer, and so do
+    block3/block4 conv2; 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass /
+    in-situ time of those launches (predecessor's end -> own end inside the CUDA-graph replay)."""
+    C = S * S
+    names = [f"k_tc_conv2[{i}]" for i in range(8)]
+    conv_us = sum(kt[n][0] for n in names if n in kt)
+    conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
+    ach = conv_flop / (conv_us * 1e-6) / 1e12
+    net_us = sum(v[0] for k, v in kt.items() if k not in ("k_step", "(fold)"))
+    flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * C / 121) * N
+    tr = traffic.get("conv_dram_bytes_per_pass") * N / 4096.0 * (C / 121.0) if traffic else None
+    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)",
+            "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+            "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
+            "timing": "in situ: %globaltimer stamps of every launch inside CUDA-graph replays of the running workload; "
+                      "a kernel's time = its predecessor's end to its own end, so the kernels partition the pass",
+            "traffic": tr,
+            "traffic_note": (traffic.get("note") + f"; scaled to {N} boards") if traffic else "no ncu capture committed for this build",
+            "algorithmic_flop_per_launch_group": conv_flop, "split_passes_issued": 3, "us_per_pass": conv_us,
+            "us_layers": {n: round(kt[n][0], 2) for n in names if n in kt},
+            "whole_net": {"kernel": "bitboards + conv1 + 8 block-conv launches + heads (11 launches)", "us_per_pass": net_us,
+                          "achieved": flop / (net_us * 1e-6) / 1e12, "frac": flop / (net_us * 1e-6) / 1e12 / pk["tensor"]}}
+
+
+def tree_roofline(kt, c0, c1, S, pk):
+    """k_step against the HBM roofline with SURVEY 8(d)'s algorithmic bytes and the run's measured d, A, f_leaf."""
+    C = S * S
+    nsims = max(1.0, c1["sims"] - c0["sims"])
+    dbar = (c1["selects"] - c0["selects"]) / nsims
+    abar = (c1["legal_sum"] - c0["legal_sum"]) / max(1.0, c1["leaf_evals"] - c0["leaf_evals"])
+    fleaf = (c1["leaf_evals"] - c0["leaf_evals"]) / nsims
+    bytes_per_sim = dbar * (12 * abar + 16 + C) + dbar * 16 + dbar * 20 + fleaf * (3 * C + 4 * C + 4 + 12 * abar + C + 16)
+    sims_per_pass = nsims / max(1.0, c1["passes"] - c0["passes"])
+    us = kt["k_step"][0]
+    gbs = bytes_per_sim * sims_per_pass / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "k_step (tree pass)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gbs / pk["hbm"], "us_per_launch": us, "bytes_per_sim": bytes_per_sim, "sims_per_launch": sims_per_pass,
+            "d_bar": dbar, "a_bar": abar, "f_leaf": fleaf}
+
+
+def measured_traffic():
+    """DRAM bytes per pass of the block convs from the committed ncu capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------
 def run_ours(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -177,10 +331,10 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import ctypes as ct
     from alphafive_b200 import _lib
-    from alphafive_b200._lib import check, ptr, stream_ptr
     from alphafive_b200.net import DeviceNet, glorot_init
+    from alphafive_b200.replay import gather_records
+    from alphafive_b200.replay_stack import RandomStack
     from alphafive_b200.selfplay import BatchedPlayer, SelfPlay
 
     S, N, sims = a.board, a.games, a.sims
@@ -189,47 +343,49 @@ def run_ours(a):
     mode = {"fp32": _lib.NET_FP32, "tc": _lib.NET_TC}.get(a.net_mode)
     if mode is None:
         mode = _lib.NET_TC if getattr(lib, "a5_net_tc_available", lambda: 0)() else _lib.NET_FP32
-    pipelined = mode == _lib.NET_TC and a.pipeline and N % 2 == 0
-    part = None
-    if pipelined:
-        from alphafive_b200.pipeline import SmPartition
-        from alphafive_b200.selfplay import PipelinedBatchedPlayer, PipelinedSelfPlay
-        try:
-            part = SmPartition.get(a.small_sms)
-        except Exception as e:                                # driver without green contexts: single stream
-            print(f"[bench] SM partition unavailable ({e}); single-stream schedule", file=sys.stderr)
-            pipelined = False
     weights = glorot_init(S, 0)
-    if pipelined:
-        sp = PipelinedSelfPlay(None, n_games=N, weights=weights, training=True, seed=0, game_id_base=rank * N,
-                               small_sms=a.small_sms, board_size=S, simulation_per_step=sims,
-                               upper_simulation_per_step=upper)
-        net, eng0, Nk = sp.nets[0], sp.halves[0].engine, N // 2           # per-kernel timing: one half
-    else:
-        net = DeviceNet(S, N, weights, mode=mode)
-        sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
-                      board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
-        eng0, Nk = sp.engine, N
-    stride = eng0.record_stride
-    rec_cap = N * 4                                          # records exchanged per step (plies finishing per step ~ N)
-    gather_out = torch.empty((world, rec_cap, stride), dtype=torch.uint8, device="cuda") if world > 1 else None
-    gather_cnt = torch.zeros(world, dtype=torch.int64, device="cuda")
+    net = DeviceNet(S, N, weights, mode=mode)
+    sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
+                  board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
+    stride = sp.engine.record_stride
+    stack = RandomStack(S, length=a.buffer)                  # the sink: every rank keeps the whole replay buffer
+    bufs = [torch.empty_like(sp.record_buf) for _ in range(2)]
+    side = torch.cuda.Stream()
+    sink = {"pending": None, "k": 0, "records": 0, "games_pushed": 0, "accepted": 0, "gather_bytes": 0, "gather_ms": 0.0,
+            "events": []}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev_nn = []
+    def drain_sink():
+        """Gather + push what the previous step harvested; runs on the side stream while the main stream
+        works through the passes already enqueued."""
+        buf = sink["pending"]
+        if buf is None:
+            return
+        sink["pending"] = None
+        with torch.cuda.stream(side):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            allrec, counts = gather_records(buf)             # count-sized: counts first, then max-count padded payload
+            e1.record()
+            flags = stack.push_records(allrec)
+            sink["events"].append((e0, e1))
+            sink["gather_bytes"] += int(counts.max()) * stride * world if world > 1 else 0
+            sink["records"] += int(allrec.shape[0])
+            sink["games_pushed"] += len(flags)
+            sink["accepted"] += sum(flags)
 
-    def one_step(timed):
-        """`sims` passes; NN forward time sampled with CUDA events every 25th pass (eager)."""
-        sp.run_passes(sims)
-        buf, games = sp.harvest()
-        if world > 1:                                        # fill every rank's replay shard (NVLink allgather)
-            cnt = torch.tensor([min(buf.shape[0], rec_cap)], dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(gather_cnt, cnt)
-            dist.all_gather_into_tensor(gather_out.view(-1), sp.record_buf[:rec_cap].reshape(-1))
+    def one_step():
+        sp.run_passes(sims)                                   # enqueued; the host is free while they run
+        drain_sink()
+        torch.cuda.current_stream().wait_stream(side)         # (after the queued passes) the buffer about to be reused is free
+        buf, games = sp.harvest(bufs[sink["k"] % 2])          # synchronises the main stream
+        sink["k"] += 1
+        side.wait_stream(torch.cuda.current_stream())         # the gather must see the harvested records
+        sink["pending"] = buf
         return buf.shape[0], games
 
     sp.start()
@@ -242,7 +398,12 @@ def run_ours(a):
         sp.harvest()
         sp.set_budget(sims, upper)
     for _ in range(a.warmup):
-        one_step(False)
+        one_step()
+    drain_sink()
+    side.synchronize()
+    for key in ("records", "games_pushed", "accepted", "gather_bytes"):
+        sink[key] = 0
+    sink["events"] = []
     c0 = sp.counters()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -252,57 +413,20 @@ def run_ours(a):
     e0.record()
     recs = 0
     for _ in range(a.steps):
-        r, _ = one_step(True)
+        r, _ = one_step()
         recs += r
+    drain_sink()                                              # the last step's records reach the buffer inside the timed region
+    torch.cuda.current_stream().wait_stream(side)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     c1 = sp.counters()
     clocks = sampler.stop() if rank == 0 else None
+    gather_ms = sum(x.elapsed_time(y) for x, y in sink["events"])
 
-    # per-kernel-class timing inside the same workload, CUDA events on the launch stream(s).  Pipelined: one
-    # half batch, block convs on the big partition, everything else on the small one -- as in the timed run.
-    reps = 20
-    if pipelined:
-        sp.pipe.drain()
-    torch.cuda.synchronize()
-    if pipelined:
-        prob, val = sp.pipe.prob[0], sp.pipe.value[0]
-        fwd = lambda parts: check(lib.a5_net_forward_parts(net.handle, ct.c_void_p(eng0.planes_ptr), Nk, ptr(prob), ptr(val),
-                                                           parts, stream_ptr()))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        body_ms = small_ms = tree_ms = 0.0
-        for _ in range(reps):
-            with torch.cuda.stream(part.small):
-                ev[0].record(); fwd(1); ev[1].record()
-            part.big.wait_stream(part.small)
-            with torch.cuda.stream(part.big):
-                ev[2].record(); fwd(2); ev[3].record()
-            part.small.wait_stream(part.big)
-            with torch.cuda.stream(part.small):
-                fwd(4); ev[4].record(); eng0.step(prob, val); ev[5].record()
-            torch.cuda.synchronize()
-            body_ms += ev[2].elapsed_time(ev[3])
-            small_ms += ev[0].elapsed_time(ev[1]) + ev[3].elapsed_time(ev[4])
-            tree_ms += ev[4].elapsed_time(ev[5])
-        body_ms /= reps; small_ms /= reps; tree_ms /= reps
-        nn_ms = body_ms + small_ms
-        c2 = sp.counters()
-        with torch.cuda.stream(part.big):
-            lt = layer_times(net, eng0.planes_ptr, Nk, prob, val)
-        torch.cuda.synchronize()
-    else:
-        prob, val = sp.prob, sp.value
-        tn0, tn1, tt0, tt1 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        nn_ms = tree_ms = 0.0
-        for _ in range(reps):
-            tn0.record(); net.forward_raw(eng0.planes_ptr, N, prob, val); tn1.record()
-            tt0.record(); eng0.step(prob, val); tt1.record()
-            torch.cuda.synchronize()
-            nn_ms += tn0.elapsed_time(tn1); tree_ms += tt0.elapsed_time(tt1)
-        nn_ms /= reps; tree_ms /= reps
-        c2 = sp.counters()
-        lt = layer_times(net, eng0.planes_ptr, N, prob, val) if mode == _lib.NET_TC else None
+    # ---- in-situ kernel accounting: the same workload, CUDA-graph replays with %globaltimer stamps ------
+    kt = sp.kernel_accounting(a.accounting_passes) if mode == _lib.NET_TC and not a.no_graph else None
+    c2 = sp.counters()
 
     t = torch.tensor([ms, float(c1["moves"] - c0["moves"]), float(c1["leaf_evals"] - c0["leaf_evals"]),
                       float(c1["sims"] - c0["sims"]), float(c1["games"] - c0["games"])], dtype=torch.float64, device="cuda")
@@ -313,53 +437,48 @@ def run_ours(a):
     else:
         ms, moves, evals, nsims, games = [x.item() for x in t]
     value = moves / (ms / 1000)
+    passes_timed = c1["passes"] - c0["passes"]
 
-    # ---- end to end through the host-buffer API (BatchedPlayer.get_actions) ----------------
-    import numpy as np
-    del sp
+    # ---- end to end through the host-buffer API (BatchedPlayer.get_actions), steady state ----------------
+    # Start from where the lock-step games stand (a stationary mix of plies), let a warm-up call build the
+    # tables, then time consecutive moves: tree reuse, budget cuts, terminal positions and restarts included.
+    e2e_steps = a.e2e_steps if a.e2e_steps is not None else max(a.steps, 8)
+    d_boards, d_last = sp.engine.roots()
+    boards, last = d_boards.cpu().numpy(), d_last.cpu().numpy()
+    launches_per_pass = 12 if mode == _lib.NET_TC else 16
+    occupancy = stack.count / stack.length
+    sp.engine.close()
+    del sp, stack, bufs
     torch.cuda.empty_cache()
-    if pipelined:
-        bp = PipelinedBatchedPlayer(None, n_players=N, weights=weights, training=True, seed=1, game_id_base=rank * N,
-                                    small_sms=a.small_sms, board_size=S, simulation_per_step=sims,
-                                    upper_simulation_per_step=upper)
-    else:
+    e2e_val, e2e_calls, bp_bytes = None, [], (0, 0)
+    if e2e_steps > 0:
         bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
                            board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
-    boards = np.zeros((N, S, S), np.int8); last = np.full(N, -1, np.int32)
-    clear = np.ones(N, np.uint8)
-    e2e_moves, e2e_t = 0, 0.0
-    for k in range(1 + a.e2e_steps):                          # first call is warm-up
-        barrier()
-        t0 = time.perf_counter()
-        pol, act, nxt, codes = bp.get_actions(boards, last, None, clear, advance=True)
-        over = codes != 0
-        boards = np.where(over[:, None, None], 0, nxt).astype(np.int8)
-        last = np.where(over, -1, act).astype(np.int32)
-        clear = over.astype(np.uint8)
-        barrier()
-        if k > 0:
-            e2e_t += time.perf_counter() - t0
-            e2e_moves += N
-    e2e = torch.tensor([e2e_t, float(e2e_moves)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        em = e2e.clone(); dist.all_reduce(em, op=dist.ReduceOp.MAX)
-        es = e2e.clone(); dist.all_reduce(es, op=dist.ReduceOp.SUM)
-        e2e_val = es[1].item() / em[0].item() if em[0].item() > 0 else None
-    else:
-        e2e_val = e2e_moves / e2e_t if e2e_t > 0 else None
+        bp_bytes = (bp.h2d_bytes, bp.d2h_bytes)
+        clear = np.ones(N, np.uint8)
+        for k in range(max(1, min(a.warmup, 2)) + e2e_steps):
+            timed = k >= max(1, min(a.warmup, 2))
+            barrier()
+            t0 = time.perf_counter()
+            pol, act, nxt, codes = bp.get_actions(boards, last, None, clear, advance=True)
+            over = codes != 0
+            boards = np.where(over[:, None, None], 0, nxt).astype(np.int8)
+            last = np.where(over, -1, act).astype(np.int32)
+            clear = over.astype(np.uint8)                    # a finished game restarts: Player.reset() (player.py:73)
+            barrier()
+            if timed:
+                e2e_calls.append(time.perf_counter() - t0)
+        e2e_t = torch.tensor([sum(e2e_calls)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_val = N * world * len(e2e_calls) / e2e_t.item()
+        bp.engine.close()
+        del bp
+        torch.cuda.empty_cache()
 
+    out = None
     if rank == 0:
         pk = peaks()
-        flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * S * S / 121)
-        nn_tflops = flop * Nk / (nn_ms / 1000) / 1e12
-        dsel = max(1, c2["sims"] - c1["sims"])
-        # SURVEY 8(d) algorithmic bytes per simulation with the measured d, A, f_leaf of this run
-        C = S * S
-        dbar = (c1["selects"] - c0["selects"]) / max(1.0, c1["sims"] - c0["sims"])
-        abar = (c1["legal_sum"] - c0["legal_sum"]) / max(1.0, c1["leaf_evals"] - c0["leaf_evals"])
-        fleaf = (c1["leaf_evals"] - c0["leaf_evals"]) / max(1.0, c1["sims"] - c0["sims"])
-        bytes_per_sim = dbar * (12 * abar + 16 + C) + dbar * 16 + dbar * 20 + fleaf * (3 * C + 4 * C + 4 + 12 * abar + C + 16)
-        tree_gbs = bytes_per_sim * dsel / reps / (tree_ms / 1000) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": "moves/s", "leaf_evals_per_s": evals / (ms / 1000),
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
@@ -368,28 +487,59 @@ def run_ours(a):
             "config": {"workload": workload_name(a, world), "board": S, "sims": sims, "upper_sims": upper,
                        "games_per_gpu": N, "net_mode": "fp32" if mode == _lib.NET_FP32 else "tc",
                        "l2": "per-pass working set (activations + node arenas) exceeds the 126 MB L2",
-                       "cuda_graph": (not a.no_graph) and not pipelined, "step": f"{sims} lock-step passes",
-                       "schedule": (f"two half batches of {Nk} games pipelined on SM-partitioned streams (CUDA green contexts: "
-                                    f"{part.n_big} SMs block convs, {part.n_small} SMs heads / tree pass / conv1)") if pipelined
-                                   else "single stream, CUDA-graph replay of one pass",
+                       "cuda_graph": not a.no_graph, "step": f"{sims} lock-step passes + harvest + record all-gather + RandomStack push",
+                       "schedule": "single stream, CUDA-graph replay of one pass; record gather + replay-buffer push on a side stream",
                        "preroll": f"{a.preroll_moves} untimed moves at {a.preroll_sims} sims to spread games over all plies"},
-            "e2e": {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": bp.h2d_bytes,
-                    "d2h_bytes_per_step": bp.d2h_bytes, "api": ("PipelinedBatchedPlayer" if pipelined else "BatchedPlayer") + ".get_actions(host boards) + device step/terminal"},
-            "gpu_launches": int((c1["passes"] - c0["passes"]) * (launches_per_pass(mode) + 1) * (2 if pipelined else 1)),
-            "roofline": roofline_entry(mode, lt, nn_ms, nn_tflops, flop, Nk, C, pk,
-                                       part=(part.n_big, part.n_small) if pipelined else None),
-            "roofline_tree": {"bound": "hbm", "kernel": "k_step (tree pass)", "achieved": tree_gbs, "peak": pk["hbm"],
-                              "unit": "GB/s", "frac": tree_gbs / pk["hbm"], "ms_per_launch": tree_ms,
-                              "bytes_per_sim": bytes_per_sim, "d_bar": dbar, "a_bar": abar, "f_leaf": fleaf},
-            "moves": moves, "sims_run": nsims, "games_finished": games, "records_per_step": recs / max(1, a.steps),
+            "e2e": {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": bp_bytes[0], "d2h_bytes_per_step": bp_bytes[1],
+                    "api": "BatchedPlayer.get_actions(host boards) + device step/terminal, consecutive moves from the "
+                           "lock-step run's positions (tree reuse, budget rule, restarts)",
+                    "calls": len(e2e_calls), "seconds": sum(e2e_calls),
+                    "moves_per_s_min": N * world / max(e2e_calls) if e2e_calls else None,
+                    "moves_per_s_max": N * world / min(e2e_calls) if e2e_calls else None},
+            "gpu_launches": int(passes_timed * launches_per_pass),
+            "ms_per_pass": ms / max(1.0, passes_timed),
+            "moves": moves, "sims_run": nsims, "games_finished": games,
+            "replay": {"records_per_step": sink["records"] / max(1, a.steps), "local_records_per_step": recs / max(1, a.steps),
+                       "games_pushed_per_step": sink["games_pushed"] / max(1, a.steps),
+                       "games_accepted_per_step": sink["accepted"] / max(1, a.steps),
+                       "allgather_bytes_per_step": sink["gather_bytes"] / max(1, a.steps),
+                       "collective_us_per_step": 1000.0 * gather_ms / max(1, a.steps),
+                       "ring_occupancy": occupancy, "buffer_plies": a.buffer,
+                       "sink": "RandomStack.push_records on every rank (utils.py:64-116 decisions, device ring)"},
             "clocks": clocks,
         }
+        if kt is not None:
+            out["kernels_us_per_pass"] = {k: [round(v[0], 2), round(v[1], 2)] for k, v in kt.items()}
+            out["kernels_note"] = ("[predecessor end -> own end, own first start -> own end] per kernel, mean over "
+                                   f"{a.accounting_passes} CUDA-graph replays right after the timed region; the first values sum to "
+                                   "the accounted pass")
+            out["roofline"] = conv_roofline(kt, S, N, pk, measured_traffic())
+            out["roofline_tree"] = tree_roofline(kt, c1, c2, S, pk)
+            out["ms_per_pass_accounted"] = sum(v[0] for v in kt.values()) / 1000.0
+        else:
+            flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * S * S / 121)
+            tf = flop * evals / (ms / 1000) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "policy/value net forward (whole pass, no per-kernel accounting)",
+                               "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"], "traffic": None}
+
+    # ---- the other BASELINE configurations ------------------------------------------------------------
+    if not a.no_configs:
+        cfgs = run_configs(a, rank, world, net, mode)
+        if rank == 0:
+            out["configs"] = cfgs
+    if rank == 0:
         if not a.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
-            cores = max(1, min((os.cpu_count() or 1) - 1, 64))
+            host = os.cpu_count() or 1
+            cores = max(1, min(host - 1, 64))
             v, ev, wall = cpu_moves_per_sec(S, sims, upper, cores, 2)
-            v5, ev5, _ = cpu_moves_per_sec(S, sims, upper, min(5, cores), 2)     # config.py:20 max_processes = 5
-            out["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-                                   "leaf_evals_per_s": ev, "five_workers": {"value": v5, "leaf_evals_per_s": ev5},
+            v5, ev5, wall5 = cpu_pipe_topology(S, sims, upper, 5, 2, net_threads=max(1, min(host - 5, 8)))
+            out["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "host_cores": host, "kind": "port",
+                                   "leaf_evals_per_s": ev,
+                                   "five_workers": {"value": v5, "leaf_evals_per_s": ev5, "workers": 5,
+                                                    "topology": "5 processes + one batching inference thread in the parent over "
+                                                                "multiprocessing Pipes (main.py:50-55, networkAPI.py:43-78)",
+                                                    "seconds": wall5},
+                                   "calibration": calibration_note(),
                                    "sample": f"{cores} processes x 2 moves of {sims} sims from the empty board, oracle port "
                                              f"(numpy MCTS + torch-CPU fp32 net, 1 thread each), {wall:.1f}s wall"}
         emit(json.dumps(out))
@@ -397,64 +547,136 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def roofline_entry(mode, lt, nn_ms, nn_tflops, flop, N, C, pk, part=None):
-    """Dominant kernel = k_tc_conv2 (eight launches per pass -- block3/block4 conv1 run as one layer, and so
-    do block3/block4 conv2 -- 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass / summed
-    CUDA-event time of those launches."""
-    whole = {"kernel": "whole net forward (bitboards + conv1 + 8 block-conv launches + heads = 11 launches)", "achieved": nn_tflops, "frac": nn_tflops / pk["tensor"],
-             "ms_per_pass": nn_ms, "flop_per_leaf": flop}
-    if lt is None:
-        return {"bound": "tensor", "kernel": "policy/value net forward, fp32 CUDA-core path", "achieved": nn_tflops,
-                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nn_tflops / pk["tensor"],
-                "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
-    conv_ms = sum(lt[1:11])
-    conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
-    ach = conv_flop / (conv_ms / 1000) / 1e12
-    tr = measured_traffic()
-    out_part = {}
-    if part:
-        out_part = {"boards_per_launch": N, "sms": part[0],
-                    "note": f"launch group of one half batch ({N} boards) on the {part[0]}-SM partition while the other "
-                            f"{part[1]} SMs run heads / tree pass / conv1 of the other half; peak is the whole chip's"}
-    traffic = tr.get("conv_dram_bytes_per_pass") * N / 4096.0 if tr else None
-    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)",
-            "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-            "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
-            "traffic": traffic, **out_part,
-            "traffic_note": (tr.get("note") + f"; scaled to {N} boards") if tr else "no ncu capture committed for this build",
-            "algorithmic_flop_per_pass": conv_flop, "issued_flop_factor": 3,
-            "ms_per_pass": conv_ms, "ms_conv1": lt[0], "ms_heads": lt[11], "ms_layers": lt[1:11],
-            "whole_net": whole}
-
-
-def launches_per_pass(mode):
-    # tensor-core path: bitboards + conv1 + 8 block-conv launches + fused dense heads; fp32 path: conv1 + 10 + 4 head kernels
-    return 11 if mode == 1 else 15
-
-
-CONV_MAC_PER_CELL = 485_376          # the ten 3x3(+1x1) block convs, MACs per board cell (58,730,496 @ 11x11)
-
-
-def layer_times(net, planes_ptr, N, prob, val, reps=10):
-    """CUDA-event time of every launch group of one net forward (ms): conv1, 10 block convs, heads."""
-    import ctypes as C
+def run_configs(a, rank, world, net11, mode):
+    """BASELINE configs 4 (15x15, 800 sims), 5 (arena, 1024 paired games at 400 sims, sharded over the ranks) and
+    1 (one game, B = 1 latency of Player.get_action).  Short legs: a few steps each."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
     from alphafive_b200 import _lib
-    from alphafive_b200._lib import check, ptr, stream_ptr
-    fn = _lib.load().a5__debug_layer_times
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
-    ms = (C.c_float * 12)()
-    check(fn(net.handle, C.c_void_p(planes_ptr), N, reps, ptr(prob), ptr(val), ms, stream_ptr()))
-    return [float(x) for x in ms]
+    from alphafive_b200.net import DeviceNet, glorot_init
+    from alphafive_b200.selfplay import SelfPlay
+    pk = peaks()
+    out = {}
 
+    def reduce(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.tolist()
 
-def measured_traffic():
-    """DRAM bytes per pass of the block convs from the committed ncu capture (profiles/traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
+    # ---- cfg 4: 4096 concurrent 15x15 games, 800 sims/move -------------------------------------------
     try:
-        return json.load(open(p))
-    except Exception:
-        return None
+        S, N, sims, upper = 15, a.games, 800, 900
+        net = DeviceNet(S, N, glorot_init(S, 0), mode=mode)
+        sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, board_size=S,
+                      simulation_per_step=sims, upper_simulation_per_step=upper)
+        sp.start()
+        sp.set_budget(40, 50)
+        sp.run_passes(32 * 40)
+        sp.harvest()
+        sp.set_budget(sims, upper)
+        sp.run_passes(sims)                                   # warm-up step
+        sp.harvest()
+        c0 = sp.counters()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        steps4 = 2
+        for _ in range(steps4):
+            sp.run_passes(sims)
+            sp.harvest()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        c1 = sp.counters()
+        kt = sp.kernel_accounting(100) if mode == _lib.NET_TC else None
+        c2 = sp.counters()
+        mx, = reduce([ms], dist.ReduceOp.MAX) if world > 1 else [ms]
+        mv, ev = reduce([c1["moves"] - c0["moves"], c1["leaf_evals"] - c0["leaf_evals"]], dist.ReduceOp.SUM) if world > 1 else \
+            [c1["moves"] - c0["moves"], c1["leaf_evals"] - c0["leaf_evals"]]
+        out["cfg4"] = {"workload": f"{N * world} concurrent 15x15 games, 800 sims/move (upper 900: the reference keeps upper = sims + 100), "
+                                   "random-init net, training-mode self-play", "moves_per_s": mv / (mx / 1000),
+                       "leaf_evals_per_s": ev / (mx / 1000), "steps": steps4, "ms_per_step": mx / steps4,
+                       "overflows": c1["overflows"], "max_nodes": c1["max_nodes"], "flop_per_leaf": FLOP_PER_LEAF[15]}
+        if kt:
+            out["cfg4"]["roofline"] = conv_roofline(kt, S, N, pk, None)
+            out["cfg4"]["roofline_tree"] = tree_roofline(kt, c1, c2, S, pk)
+            out["cfg4"]["kernels_us_per_pass"] = {k: [round(v[0], 2), round(v[1], 2)] for k, v in kt.items()}
+        sp.engine.close()
+        net.close()
+        del sp, net
+        torch.cuda.empty_cache()
+    except Exception as e:                                    # a side leg must not take the headline down
+        out["cfg4"] = {"error": repr(e)}
+
+    # ---- cfg 5: arena, 1024 paired games between two weight sets, 400 sims/move ----------------------
+    try:
+        import types
+        from alphafive_b200 import config as cfgmod
+        from alphafive_b200.drivers import Arena, count_wins
+        from alphafive_b200.replay import allreduce_wins
+        S, total, sims = 11, 1024, 400
+        n_local = total // world
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt6960.npz"))
+        w_a = {k.replace("__", "/"): z[k] for k in z.files}
+        net_a = DeviceNet(S, n_local, w_a, mode=mode)
+        net_b = DeviceNet(S, n_local, glorot_init(S, 0), mode=mode)
+        cfg = types.SimpleNamespace(**{k: getattr(cfgmod, k) for k in dir(cfgmod) if not k.startswith("_")})
+        cfg.board_size, cfg.simulation_per_step, cfg.upper_simulation_per_step = S, sims, sims + 242   # choose_best_player.py:25: 400 of 642
+        arena = Arena(cfg, net_a, net_b, n_local, seed=7, game_id_base=rank * n_local)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = arena.play()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        winners = res["winners"]
+        w0, w1, dr = allreduce_wins(int((winners == 0).sum()), int((winners == 1).sum()), int((winners < 0).sum()), device="cuda")
+        mx, = reduce([dt], dist.ReduceOp.MAX) if world > 1 else [dt]
+        mv, ev = reduce([res["moves"], res["leaf_evals"]], dist.ReduceOp.SUM) if world > 1 else [res["moves"], res["leaf_evals"]]
+        e0_, e1_, counted = count_wins(winners.tolist())      # the reference's sequential early-stop rule on this rank's games
+        out["cfg5"] = {"workload": f"arena: {total} paired games to completion ({n_local}/GPU), {sims} sims/move, ckpt-6960 vs glorot "
+                                   "seed 0, Player(training=False).get_action(random_a=True), separate table per player "
+                                   "(choose_best_player.py:24-72)",
+                       "wins_ckpt6960": w0, "wins_glorot": w1, "draws": dr, "moves_per_s": mv / mx, "leaf_evals_per_s": ev / mx,
+                       "seconds": mx, "mean_plies": float(res["plies"].mean()),
+                       "early_stop_rule_rank0": {"wins0": e0_, "wins1": e1_, "games_counted": counted},
+                       "collective": "allreduce_wins (3 int64, NCCL)" if world > 1 else "none (1 GPU)"}
+        arena.close()
+        net_a.close(); net_b.close()
+        del arena, net_a, net_b
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["cfg5"] = {"error": repr(e)}
+
+    # ---- cfg 1 on the GPU: one game, Player.get_action latency (B = 1) -------------------------------
+    if rank == 0:
+        try:
+            import types
+            from alphafive_b200 import config as cfgmod
+            from alphafive_b200.genData.network import ResNet
+            from alphafive_b200.genData.player import Player, board_to_state, state_to_board
+            cfg = types.SimpleNamespace(**{k: getattr(cfgmod, k) for k in dir(cfgmod) if not k.startswith("_")})
+            cfg.board_size, cfg.simulation_per_step, cfg.upper_simulation_per_step = 11, 500, 642
+            rn = ResNet(11, max_batch=8, seed=0)
+            pl = Player(cfg, training=False, pv_fn=rn.eval)
+            state, lat = pl.get_init_state(), []
+            from alphafive_b200 import utils as a5utils
+            for ply in range(7):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                _, action = pl.get_action(state, last_action=None)          # self_play.py:95-97 resets last_action
+                lat.append(time.perf_counter() - t0)
+                board = a5utils.step(state_to_board(state, 11), action)
+                state = board_to_state(board)
+            pl.close()
+            rn.close()
+            out["cfg1_gpu"] = {"workload": "single 11x11 game, 500 sims/move, random-init net, Player(training=False).get_action "
+                                           "with the on-device net (self_play.py:94-101)", "ms_per_move": 1000 * float(np.mean(lat[1:])),
+                               "ms_first_move": 1000 * lat[0], "moves_per_s": 1.0 / float(np.mean(lat[1:])), "moves_timed": len(lat) - 1}
+        except Exception as e:
+            out["cfg1_gpu"] = {"error": repr(e)}
+    return out
 
 
 def emit(line: str):

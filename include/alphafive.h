@@ -152,6 +152,10 @@ int a5_engine_root_stats(a5_engine* e, int32_t* d_n, float* d_w, float* d_p, int
 int a5_engine_node_stats(a5_engine* e, const int8_t* d_boards, int32_t* d_n, float* d_w, float* d_p,
                          int32_t* d_sum_n, void* stream);
 
+/* The current root position of every game (Player.root_state, player.py:30,138) and the move that led to it:
+ * d_boards int8[N][S*S], d_last int32[N] (may be NULL).  In auto_play mode this is where each game stands. */
+int a5_engine_get_roots(a5_engine* e, int8_t* d_boards, int32_t* d_last, void* stream);
+
 /* Player.tau of every game (player.py:32,108-111): double[N] on the device, decayed by finish_move. */
 double* a5_engine_tau(a5_engine* e);
 

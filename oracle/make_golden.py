@@ -501,7 +501,6 @@ def main():
         return
     if "--games-only" in sys.argv:
         make_games()
-    make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
         return
     if "--games300-only" in sys.argv:
         make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")

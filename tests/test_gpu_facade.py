@@ -174,7 +174,7 @@ def test_player_tree_view_pruning_and_reset(cuda_lib):
         assert node.sum_n == sum_n and set(node.a) == set(orules.legal_actions(board))
         for (i, j), e in node.a.items():
             c = i * S + j
-            assert e.n == n[c] and e.w == w[c] and e.p == p[c] and (e.q == w[c] / n[c] if n[c] else e.q == 0)
+            assert e.n == n[c] and e.w == w[c] and e.p == p[c] and (e.q == w[c] / np.float32(n[c]) if n[c] else e.q == 0)
         with pytest.raises(KeyError):
             tree["x" + state]
         nxt = orules.play(board, action)
@@ -202,5 +202,5 @@ def test_player_engine_follows_budget_growth(cuda_lib):
     opl = omcts.OraclePlayer(omcts.SearchConfig(simulation_per_step=3000, upper_simulation_per_step=3100),
                              training=False, pv_fn=pv)
     assert opl.get_action(np.zeros((11, 11), np.int8), None)[1] == action
-    assert pl.tree[s0].sum_n == 3000
+    assert pl.tree[s0].sum_n == 2999                     # the first simulation expands the root, the other 2999 select from it
     pl.close()

@@ -91,8 +91,11 @@ def test_matches_oracle_on_many_roots_with_device_net(cuda_lib):
     eng.run_search(net=net, check_every=4)
     n = eng.root_stats()[0].cpu().numpy()
     onet_ = onet.OracleNet(S, w)
-    same = 0
+    same = checked = 0
     for j in range(48):
+        if not boards[j].any():
+            continue          # the empty board: all-zero input + zero biases = exactly uniform prior, a 121-way tie (random pick)
+        checked += 1
         la = tuple(int(v) for v in last[j])
         la = la if la[0] >= 0 else None
         cfg = omcts.SearchConfig(simulation_per_step=sims, upper_simulation_per_step=sims + 100)
@@ -103,7 +106,7 @@ def test_matches_oracle_on_many_roots_with_device_net(cuda_lib):
         pl.get_action(boards[j], la)
         same += int((pl.root_stats(boards[j])[0] == n[j]).all())
         assert n[j].sum() == sims - 1
-    assert same >= 44, same
+    assert checked >= 46 and same >= checked - 3, (same, checked)
 
 
 def test_training_mode_distribution(cuda_lib):
