@@ -53,9 +53,11 @@ struct TCLayer {
   int reverse;                   // 1: walk the groups from the last to the first.  Layers alternate direction so
                                  // that each starts on the rows its predecessor touched last: ~100 MB of every
                                  // 150-450 MB activation tensor are then still in the 126 MB L2
+  uint32_t lo_add, lo_mask;      // rounding of the lo halves to fewer mantissa bits (a5_tc_state::lo_drop), both fp16 lanes
   int nslab_buf, w_bytes;        // pair kernel: A slab buffers, bytes of the weight region (ring or resident set)
   unsigned long long* dbg;       // tooling: clock64 timeline of CTA 0 (4 roles x 256 slots), or null
   unsigned long long* kt;        // tooling: in-situ kernel timing slot (common.cuh), or null
+  unsigned long long* clk;       // tooling: {clock64, globaltimer} at start and end of CTA 0 (SM clock of this launch), or null
   // fused 1x1 head conv + ELU in the epilogue (network.py:69-70 value, :81-82 policy): the
   // layer's own activation is then not stored; the head output goes out as the A operand of
   // the dense layer that follows (k_tc_fc), K ordered (cell, channel).
@@ -281,7 +283,7 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
             const float2 hf = __half22float2(h);
             const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
             hi[e] = real ? *(const uint32_t*)&h : 0u;
-            lo[e] = real ? *(const uint32_t*)&l : 0u;
+            lo[e] = real ? ((*(const uint32_t*)&l + L.lo_add) & L.lo_mask) : 0u;
           }
           const bool second = L.out2 && c0 >= L.split;
           __half* ob = second ? L.out2 : L.out;
@@ -450,6 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
 
   pdl_launch_dependents();
   kt_begin(L.kt);
+  if (L.clk && blockIdx.x == 0 && threadIdx.x == 0) { L.clk[0] = (unsigned long long)clock64(); L.clk[1] = kt_now(); }
   if (threadIdx.x < cout) s_bias[threadIdx.x] = L.bias[threadIdx.x] * ACT_SCALE;
   if (L.head_ch) {
     for (int i = threadIdx.x; i < 32 * L.head_ch; i += TC2_THREADS) s_hw[i] = L.head_w[i];
@@ -690,6 +693,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   __syncthreads();
   cluster_sync_all();                                      // nobody leaves while the peer may still touch its barriers / smem
   kt_end(L.kt);
+  if (L.clk && blockIdx.x == 0 && threadIdx.x == 0) { L.clk[2] = (unsigned long long)clock64(); L.clk[3] = kt_now(); }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -698,8 +702,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
 
 // One 3x3 / 1x1 segment of a merged layer, non-fold layout: per stage (32-channel slab, tap) the shares of the two
 // CTAs, each [kchunk 4][X: n/2 rows of w_hi | S: n/2 rows of w_lo][8].  `wb` (optional) continues `w` along N.
+__device__ __forceinline__ __half lo_round(__half l, int drop) {
+  if (!drop) return l;
+  unsigned short b = *(unsigned short*)&l;
+  b = (unsigned short)((b + (1u << (drop - 1))) & ~((1u << drop) - 1u));
+  return *(__half*)&b;
+}
 __global__ void k_tc_pack2_seg(const float* __restrict__ w, const float* __restrict__ wb, int na, int ntaps, int cin, int n,
-                               __half* __restrict__ out) {
+                               __half* __restrict__ out, int drop) {
   const int nstages = (cin / TC_KS) * ntaps;
   const long long per_cta = (long long)4 * n * 8;          // halfs
   const long long total = (long long)nstages * 2 * per_cta;
@@ -716,7 +726,7 @@ __global__ void k_tc_pack2_seg(const float* __restrict__ w, const float* __restr
     float x = !wb ? w[kk * n + col] : (col < na ? w[kk * na + col] : wb[kk * (n - na) + (col - na)]);
     x *= W_SCALE;
     const __half h = __float2half_rn(x);
-    out[i] = lo ? __float2half_rn(x - __half2float(h)) : h;
+    out[i] = lo ? lo_round(__float2half_rn(x - __half2float(h)), drop) : h;
   }
 }
 
@@ -724,7 +734,7 @@ __global__ void k_tc_pack2_seg(const float* __restrict__ w, const float* __restr
 // `wb` (optional): a second kernel over the same input whose output channels follow the `na` of `w`
 // (two convs of one tensor merged into one layer).
 __global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict__ wb, int na, const float* __restrict__ wres,
-                           int ntaps, int cin, int rcin, int cout, int fold, __half* __restrict__ out) {
+                           int ntaps, int cin, int rcin, int cout, int fold, __half* __restrict__ out, int drop) {
   const int main_stages = (cin / TC_KS) * ntaps;
   const int nstages = main_stages + (wres ? rcin / TC_KS : 0);
   const int xr = fold ? cout : cout / 2, sr = cout / 2, rows = xr + sr;
@@ -756,7 +766,7 @@ __global__ void k_tc_pack2(const float* __restrict__ w, const float* __restrict_
     }
     x *= W_SCALE;
     const __half h = __float2half_rn(x);
-    out[i] = lo ? __float2half_rn(x - __half2float(h)) : h;
+    out[i] = lo ? lo_round(__float2half_rn(x - __half2float(h)), drop) : h;
   }
 }
 
@@ -815,7 +825,8 @@ __global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ plan
 __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __restrict__ bits, const __half* __restrict__ wpk,
                                                           const float* __restrict__ bias, __half* __restrict__ out,
                                                           long long plane_rows, int S, int pitch, int per_board, int guard,
-                                                          int n, int ntiles, unsigned long long* kt) {
+                                                          int n, int ntiles, uint32_t lo_add, uint32_t lo_mask,
+                                                          unsigned long long* kt) {
   extern __shared__ __align__(128) uint8_t smem[];
   kt_begin(kt);
   uint8_t* a_buf = smem;                                       // 2 A tiles [kchunk 10][row 128][8]
@@ -965,7 +976,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
             const float2 hf = __half22float2(hh);
             const __half2 ll = __floats2half2_rn(x[0] - hf.x, x[1] - hf.y);
             hi[e] = real ? *(const uint32_t*)&hh : 0u;
-            lo[e] = real ? *(const uint32_t*)&ll : 0u;
+            lo[e] = real ? ((*(const uint32_t*)&ll + lo_add) & lo_mask) : 0u;
           }
           const long long chunk = h2 * 2 + kc;
           *(uint4*)(out + (chunk * plane_rows + row) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -1080,6 +1091,12 @@ struct a5_tc_state {
   int zigzag = 1;               // A5_TC_ZIGZAG=0: every layer walks the groups in ascending order
   int resw = 1;                 // A5_TC_RESW=0: always stream weights through the stage ring
   int pdl = 1;                  // A5_TC_PDL=0: plain stream-ordered launches
+  // The lo halves of activations and conv weights are rounded to 10 - lo_drop mantissa bits (default 4: 6 bits, an
+  // operand = 11 + 7 significant bits).  The chip is power-capped under tensor load and the clock follows the
+  // switching activity of the multiplier arrays: fewer significant bits in two of the three passes = +3 % clock,
+  // with no measurable change of the output error (profiles/r02_lo_bits.txt).  A5_TC_LO_DROP=0..8 overrides.
+  int lo_drop = 4;
+  uint32_t lo_add = 0, lo_mask = 0xFFFFFFFFu;   // both fp16 lanes of a packed pair
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
   int fold = 1;
@@ -1146,6 +1163,12 @@ int tc_alloc(a5_net* net) {
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge2 = ((ev = getenv("A5_TC_MERGE2")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
+  if ((ev = getenv("A5_TC_LO_DROP")) && atoi(ev) >= 0 && atoi(ev) <= 8) tc->lo_drop = atoi(ev);
+  {
+    const uint32_t d = (uint32_t)tc->lo_drop, r = d ? (1u << (d - 1)) : 0u, m = ~((1u << d) - 1u) & 0xFFFFu;
+    tc->lo_add = r | (r << 16);
+    tc->lo_mask = m | (m << 16);
+  }
   int hrc = heads_alloc(net, &tc->heads);
   if (hrc) return hrc;
   int dev = 0;
@@ -1177,21 +1200,21 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
     const int t0 = kBlocks[(l - 1) / 2].t0;
     const float* w = (l & 1) ? t[t0 + 2] : t[t0 + 4];
     const float* wres = (l & 1) ? nullptr : t[t0 + 0];
-    k_tc_pack2<<<256, 256, 0, st>>>(w, nullptr, 0, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l]);
+    k_tc_pack2<<<256, 256, 0, st>>>(w, nullptr, 0, wres, 9, L.cin, L.res_cin, L.cout, (L.cout <= 64) ? tc->fold : 0, tc->wpk2[l], tc->lo_drop);
     A5_CUDA(cudaGetLastError());
   }
   k_c1m_pack<<<(C1M_KCH * 64 * 8 + 255) / 256, 256, 0, st>>>(net->w[0], 64, tc->wpk_c1);
   A5_CUDA(cudaGetLastError());
-  k_tc_pack2<<<256, 256, 0, st>>>(t[T_B3_C1_K], t[T_B4_C1_K], 32, nullptr, 9, 128, 0, 96, 0, tc->wpk2_m);
+  k_tc_pack2<<<256, 256, 0, st>>>(t[T_B3_C1_K], t[T_B4_C1_K], 32, nullptr, 9, 128, 0, 96, 0, tc->wpk2_m, tc->lo_drop);
   A5_CUDA(cudaGetLastError());
   A5_CUDA(cudaMemcpyAsync(tc->bias_m, net->bias[5], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A5_CUDA(cudaMemcpyAsync(tc->bias_m + 32, net->bias[7], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   {
     // merged conv2 layer: [block3-conv2 3x3 | block4-conv2 3x3 | (block3-res | block4-res) 1x1]
     uint8_t* base = (uint8_t*)tc->wpk2_m2;
-    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_C2_K], nullptr, 0, 9, 32, 32, (__half*)base);
-    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B4_C2_K], nullptr, 0, 9, 64, 64, (__half*)(base + 2 * 9 * 2048));
-    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_RES_K], t[T_B4_RES_K], 32, 1, 128, 96, (__half*)(base + 2 * (9 * 2048 + 18 * 4096)));
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_C2_K], nullptr, 0, 9, 32, 32, (__half*)base, tc->lo_drop);
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B4_C2_K], nullptr, 0, 9, 64, 64, (__half*)(base + 2 * 9 * 2048), tc->lo_drop);
+    k_tc_pack2_seg<<<64, 256, 0, st>>>(t[T_B3_RES_K], t[T_B4_RES_K], 32, 1, 128, 96, (__half*)(base + 2 * (9 * 2048 + 18 * 4096)), tc->lo_drop);
     A5_CUDA(cudaGetLastError());
     A5_CUDA(cudaMemcpyAsync(tc->bias_m2, net->bias[6], 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     A5_CUDA(cudaMemcpyAsync(tc->bias_m2 + 32, net->bias[8], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1203,6 +1226,7 @@ int tc_set_weights(a5_net* net, const float* const* t, cudaStream_t st) {
 static cudaEvent_t* g_tc_events = nullptr;
 static bool g_tc_keep_head_acts = false;           // a5__debug_activation wants block3/5 outputs stored too
 static unsigned long long* g_tc_dbg = nullptr;   // a5__debug_timeline: [10 layers][4 roles][256]
+static unsigned long long* g_tc_clk = nullptr;   // a5__debug_clk: [8 conv launches][4]
 #define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
 
 // heads + biases come from the fp32 path's packed copies (fp32_set_weights runs first)
@@ -1217,7 +1241,8 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits, kt_slot(KT_C1BITS));
     A5_CUDA(cudaGetLastError());
     k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
-                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles, kt_slot(KT_CONV1));
+                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles, tc->lo_add, tc->lo_mask,
+                                                     kt_slot(KT_CONV1));
   }
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);
@@ -1260,7 +1285,9 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     L.reverse = tc->zigzag && (nexec++ % 2 == 0);
     L.dbg = g_tc_dbg ? g_tc_dbg + (size_t)(l - 1) * 8 * 256 : nullptr;
     L.kt = kt_slot(KT_CONV0 + (nexec - 1));
+    L.clk = g_tc_clk ? g_tc_clk + 4 * (nexec - 1) : nullptr;
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
+    L.lo_add = tc->lo_add; L.lo_mask = tc->lo_mask;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
     {
       // CTA pairs: T = 2 tiles per CTA, 4 per weight stage; TMEM double-buffers for every layer
@@ -1355,6 +1382,10 @@ int a5__debug_ktime_read(double* h_out) {
   for (int i = 0; i < KT_SLOTS * 3; ++i) h_out[i] = (double)acc[i];
   return A5_OK;
 }
+
+// internal tooling: device buffer uint64 [8][4] receiving {clock64, globaltimer} at start / end of CTA 0 of every
+// block-conv launch from now on (null: off) -- the SM clock each layer actually ran at
+int a5__debug_clk(unsigned long long* d_buf) { g_tc_clk = d_buf; return A5_OK; }
 
 // internal tooling: also store the block3 / block5 activations (normally consumed in-register by
 // the fused head convs) so a5__debug_activation can show them.
