@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libalphafive.so")
 NUM_COUNTERS = 16
 NUM_TENSORS = 42
-NET_FP32, NET_TC = 0, 1
+NET_FP32, NET_TC, NET_SMALL = 0, 1, 2
+NET_SMALL_MAX = 8
 
 
 class A5Error(RuntimeError):

@@ -4,6 +4,7 @@
 #include "net_common.cuh"
 
 struct a5_tc_state;   // tensor-core path (net_tc.cu)
+namespace a5 { struct SmallState; }   // small-batch latency path (net_small.cu)
 
 struct a5_net {
   int S = 0, C = 0, max_batch = 0;
@@ -22,6 +23,8 @@ struct a5_net {
   int ldl = 0;
   // ---- tensor-core path ------------------------------------------------------
   a5_tc_state* tc = nullptr;
+  // ---- small-batch latency path (shares the fp32 path's matrices and activation buffers) ----
+  a5::SmallState* sm = nullptr;
 };
 
 namespace a5 {
@@ -39,6 +42,11 @@ int heads_forward(a5_net* net, HeadsState* h, int n, float* prob, float* value, 
 // conv-epilogue side of the heads: where the fused 1x1 head convs write, and their weights
 struct HeadsIO { __half* a_pol; __half* a_val; const float* pconv_w; const float* pconv_b; int nst_pol, nst_val; };
 HeadsIO heads_io(const HeadsState* h);
+
+int small_alloc(a5_net* net, SmallState** out);
+void small_free(SmallState* s);
+int small_set_weights(a5_net* net, SmallState* s, cudaStream_t st);
+int small_forward(a5_net* net, SmallState* s, const int8_t* planes, int n, float* prob, float* value, cudaStream_t st);
 
 int tc_alloc(a5_net* net);
 void tc_free(a5_net* net);

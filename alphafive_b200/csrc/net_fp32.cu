@@ -475,6 +475,7 @@ int a5_net_create(int S, int max_batch, a5_net** out) {
   net->S = S; net->C = S * S; net->max_batch = max_batch;
   int rc = fp32_alloc(net);
   if (rc == A5_OK) rc = tc_alloc(net);
+  if (rc == A5_OK) rc = small_alloc(net, &net->sm);
   if (rc != A5_OK) { a5_net_destroy(net); return rc; }
   *out = net;
   return A5_OK;
@@ -484,6 +485,7 @@ int a5_net_destroy(a5_net* net) {
   if (!net) return A5_OK;
   fp32_free(net);
   tc_free(net);
+  small_free(net->sm);
   delete net;
   return A5_OK;
 }
@@ -493,6 +495,7 @@ int a5_net_set_weights(a5_net* net, const float* const* d_tensors, void* stream)
   for (int i = 0; i < A5_NET_NUM_TENSORS; ++i) A5_ARG(d_tensors[i] != nullptr);
   int rc = fp32_set_weights(net, d_tensors, (cudaStream_t)stream);
   if (rc == A5_OK) rc = tc_set_weights(net, d_tensors, (cudaStream_t)stream);
+  if (rc == A5_OK) rc = small_set_weights(net, net->sm, (cudaStream_t)stream);
   if (rc == A5_OK) net->has_weights = true;
   return rc;
 }
@@ -503,6 +506,10 @@ int a5_net_forward(a5_net* net, const int8_t* d_planes, int n, float* d_prob, fl
   if (n == 0) return A5_OK;
   if (mode == A5_NET_FP32) return fp32_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream);
   if (mode == A5_NET_TC) return tc_forward(net, d_planes, n, d_prob, d_value, (cudaStream_t)stream);
+  if (mode == A5_NET_SMALL) {
+    if (n > A5_NET_SMALL_MAX) { set_error("a5_net_forward: A5_NET_SMALL takes at most %d boards, got %d", A5_NET_SMALL_MAX, n); return A5_ERR_ARG; }
+    return small_forward(net, net->sm, d_planes, n, d_prob, d_value, (cudaStream_t)stream);
+  }
   set_error("a5_net_forward: unknown mode %d", mode);
   return A5_ERR_ARG;
 }

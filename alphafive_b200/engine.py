@@ -159,9 +159,9 @@ class SearchEngine:
         return buf[:cnt.value], games.value
 
     # -- convenience: run until every game's budget is spent (auto_play = 0) ------
-    def run_search(self, net=None, pv_fn=None, check_every: int = 16):
+    def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None):
         """Drive step/forward until no game is busy.  ``net`` is a DeviceNet (on-device
-        leaf evaluation); ``pv_fn`` is a reference-style host callable."""
+        leaf evaluation, ``net_mode`` overrides its compute path); ``pv_fn`` is a reference-style host callable."""
         assert (net is None) != (pv_fn is None)
         prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
         value = torch.empty((self.N,), dtype=torch.float32, device=self.device)
@@ -189,7 +189,7 @@ class SearchEngine:
                 # bounds the first burst when the budgets are not known to be small)
                 left = max(1, int(self.sims_left().max().item()))
                 for _ in range(left):
-                    net.forward_raw(self.planes_ptr, self.N, prob, value)
+                    net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
                     self.step(prob, value)
                 it += left
                 if self.busy() == 0:

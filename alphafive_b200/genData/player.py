@@ -119,6 +119,8 @@ class Player(object):
         self._engine = None
         self._budget = None
         self._clear = True
+        from .._lib import NET_SMALL
+        self.net_mode = NET_SMALL                    # compute path of an on-device pv_fn (None: the net's own)
 
     # ------------------------------------------------------------------ engine plumbing
     def _eng(self) -> SearchEngine:
@@ -192,7 +194,8 @@ class Player(object):
                       np.array([1 if self._clear else 0], np.uint8))
         self._clear = False
         net, fn = self._leaf_fn()
-        eng.run_search(net=net, pv_fn=fn, check_every=8)
+        # one board, strictly sequential leaf evaluations: the one-kernel latency path of the device net
+        eng.run_search(net=net, pv_fn=fn, check_every=8, net_mode=None if net is None else self.net_mode)
         try:
             eng.counters()                            # raises A5_ERR_CAPACITY if an expansion did not fit
         except A5Error as err:

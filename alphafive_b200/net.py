@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NET_FP32, NET_TC, check, ptr, stream_ptr
+from ._lib import NET_FP32, NET_SMALL, NET_SMALL_MAX, NET_TC, check, ptr, stream_ptr  # noqa: F401
 
 
 def tensor_names():
@@ -52,7 +52,9 @@ def glorot_init(S: int, seed: int = 0) -> dict[str, np.ndarray]:
 
 class DeviceNet:
     """eval(planes) -> (prob, value) on the device.  ``mode``: ``NET_TC`` (default) is the tcgen05 path;
-    ``NET_FP32`` is the exact-fp32 CUDA-core path kept as the on-device reference for debugging."""
+    ``NET_FP32`` is the exact-fp32 CUDA-core path kept as the on-device reference for debugging; ``NET_SMALL``
+    (per call, at most ``NET_SMALL_MAX`` boards) is the one-kernel fp32 latency path a single ``Player`` search
+    evaluates its leaves with."""
 
     def __init__(self, S: int, max_batch: int, weights: dict | None = None, mode: int = NET_TC, device=None):
         self.lib = _lib.load()

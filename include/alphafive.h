@@ -225,6 +225,11 @@ int64_t a5_net_tensor_size(int i, int S);
 #define A5_NET_FP32 0            /* fp32 CUDA-core path                              */
 #define A5_NET_TC   1            /* tcgen05 tensor-core path, fp16 hi/lo split (3 MMA
                                     passes, fp32 accumulate)                         */
+#define A5_NET_SMALL 2           /* latency path for n <= A5_NET_SMALL_MAX boards: the
+                                    whole forward as one persistent fp32 kernel -- the
+                                    leaf evaluation of ONE Player.get_action search
+                                    (player.py:128-147, 190-192; GUI.py:124-167)      */
+#define A5_NET_SMALL_MAX 8
 
 int a5_net_create(int S, int max_batch, a5_net** out);
 int a5_net_destroy(a5_net* net);

@@ -58,6 +58,40 @@ def test_random_init_parity(cuda_lib, S, mode):
     np.testing.assert_allclose(got_p.sum(1), 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("S", [11, 15])
+def test_small_batch_latency_path_parity(cuda_lib, S):
+    """A5_NET_SMALL (one persistent fp32 kernel, the leaf evaluator of a single Player search): exact fp32, so it
+    sits within fp32 summation-order noise of the oracle -- well inside the 1e-4 bar -- for every batch 1..8,
+    on the trained checkpoint (11x11) and random-init weights, and repeats bit for bit."""
+    from alphafive_b200 import _lib
+    from alphafive_b200.net import DeviceNet, glorot_init
+    rng = np.random.default_rng(100 + S)
+    if S == 11:
+        g = golden("replay_sample.npz")
+        x = _planes(g["boards"][:40], g["last_action"][:40])
+        w = _ckpt()
+    else:
+        boards = np.stack([orules.random_board(rng, S) for _ in range(40)])
+        x = _planes(boards, np.full((40, 2), -1))
+        w = glorot_init(S, seed=0)
+    want_p, want_v = onet.OracleNet(S, w).eval(x)
+    net = DeviceNet(S, 16, w)
+    xs = torch.from_numpy(np.ascontiguousarray(x > 0.5)).to(torch.int8).cuda()
+    i = 0
+    for n in (1, 2, 3, 8, 1, 5, 8, 4, 8):
+        p, v = net.forward(xs[i:i + n], mode=_lib.NET_SMALL)
+        p2, v2 = net.forward(xs[i:i + n], mode=_lib.NET_SMALL)
+        assert torch.equal(p, p2) and torch.equal(v, v2)
+        p, v = p.cpu().numpy(), v.cpu().numpy()
+        assert np.abs(p - want_p[i:i + n]).max() <= 2e-5, (n, np.abs(p - want_p[i:i + n]).max())
+        assert np.abs(v - want_v[i:i + n]).max() <= 2e-5, (n, np.abs(v - want_v[i:i + n]).max())
+        np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+        i += n
+    from alphafive_b200._lib import A5Error
+    with pytest.raises(A5Error):
+        net.forward(xs[:9], mode=_lib.NET_SMALL)
+
+
 def test_eval_is_the_reference_pv_fn_seam(cuda_lib):
     """ResNet.eval contract (network.py:90-97): f32 [B,3,S,S] -> (f32 [B,S*S], f32 [B])."""
     from alphafive_b200.net import DeviceNet
