@@ -58,6 +58,13 @@ class SearchEngine:
         self.planes_ptr = self.lib.a5_engine_planes(h)
         self.record_stride = self.lib.a5_record_stride(self.S)
         self._first = True
+        # CUDA graph of one search pass (leaf evaluation + tree pass) for run_search: kernel parameters are baked
+        # into it, so it is keyed on the net, its compute path and a version that set_mode / set_budget bump
+        self._version = 0
+        self._graph = None
+        self._graph_key = None
+        self._prob = self._value = None
+        self.use_graph = os.environ.get("A5_SEARCH_GRAPH", "1") != "0"
 
     # -- raw passes -----------------------------------------------------------
     def reset(self):
@@ -76,9 +83,11 @@ class SearchEngine:
 
     def set_mode(self, training: bool, random_a: bool = False):
         check(self.lib.a5_engine_set_mode(self.handle, int(training), int(random_a)))
+        self._version += 1
 
     def set_budget(self, sims: int, upper: int):
         check(self.lib.a5_engine_set_budget(self.handle, int(sims), int(upper)))
+        self._version += 1
 
     def step(self, prob=None, value=None):
         if self._first:
@@ -163,8 +172,10 @@ class SearchEngine:
         """Drive step/forward until no game is busy.  ``net`` is a DeviceNet (on-device
         leaf evaluation, ``net_mode`` overrides its compute path); ``pv_fn`` is a reference-style host callable."""
         assert (net is None) != (pv_fn is None)
-        prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
-        value = torch.empty((self.N,), dtype=torch.float32, device=self.device)
+        if self._prob is None:
+            self._prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+            self._value = torch.empty((self.N,), dtype=torch.float32, device=self.device)
+        prob, value = self._prob, self._value
         it = 0
         self.step()
         while True:
@@ -188,10 +199,26 @@ class SearchEngine:
                 # then look again (games that met terminal positions finished early; `check_every` only
                 # bounds the first burst when the budgets are not known to be small)
                 left = max(1, int(self.sims_left().max().item()))
-                for _ in range(left):
+                it += left
+                key = (id(net), net_mode, self._version)
+                if self.use_graph and left >= 4 and self._graph_key != key:
+                    # one eager pass (counts), then capture the pass; replays keep the launch gaps off the GPU
                     net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
                     self.step(prob, value)
-                it += left
+                    left -= 1
+                    torch.cuda.current_stream().synchronize()
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
+                        self.step(prob, value)
+                    self._graph_key = key
+                if self.use_graph and self._graph_key == key:
+                    for _ in range(left):
+                        self._graph.replay()
+                else:
+                    for _ in range(left):
+                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
+                        self.step(prob, value)
                 if self.busy() == 0:
                     break
                 continue
@@ -199,6 +226,8 @@ class SearchEngine:
         return it
 
     def close(self):
+        self._graph = None
+        self._graph_key = None
         if self.handle:
             self.lib.a5_engine_destroy(self.handle)
             self.handle = None
