@@ -30,6 +30,35 @@ void set_error(const char* fmt, ...);
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of a search pass lets its successor be scheduled at once
+// (griddepcontrol.launch_dependents at its top: the successor's CTAs take SMs as this grid's CTAs exit and run
+// their prologue behind its tail) and waits for its predecessor (griddepcontrol.wait: completion + memory
+// visibility) right before it first touches the predecessor's output.  Every kernel of the chain executes the
+// wait, so "my predecessor is complete" is transitive along the stream.  Without the launch attribute (or after a
+// memcpy) both instructions are no-ops.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();                             // A5_TC_PDL=0 turns every programmatic launch attribute off (engine.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_k(void (*kernel)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
+                                       bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // In-situ kernel timing (a5__debug_ktime_*): every kernel of a self-play pass can stamp %globaltimer when
 // its first thread starts and when each CTA has finished, into its slot of a device buffer
 // [slot][32 sub-slots][start_min, end_max]; a fold kernel at the end of the pass turns the stamps into

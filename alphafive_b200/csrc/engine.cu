@@ -794,6 +794,8 @@ __global__ void __launch_bounds__(WPB * 32, A5_STEP_MINB) k_step(const __grid_co
   __shared__ __align__(16) int8_t s_board[WPB][256];
   __shared__ __align__(16) float s_f[WPB][256];
   __shared__ uint32_t s_valid[WPB][4 * NCH];
+  pdl_launch_dependents();
+  pdl_wait();                                              // the heads kernel that wrote prob / value is complete
   kt_begin(P.kt);
   step_body<NCH>(P, prob, value, s_board, s_f, s_valid);
   if (P.kt) { __syncthreads(); kt_end(P.kt); }
@@ -998,6 +1000,13 @@ struct a5_engine {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+namespace a5 {
+bool pdl_enabled() {
+  static const bool on = [] { const char* ev = getenv("A5_TC_PDL"); return !(ev && atoi(ev) == 0); }();
+  return on;
+}
+}  // namespace a5
+
 extern "C" {
 
 int a5_record_stride(int S) {
@@ -1130,7 +1139,9 @@ int a5_engine_set_roots(a5_engine* e, const int8_t* d_boards, const int32_t* d_l
 int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void* stream) {
   A5_ARG(e && ((d_prob == nullptr) == (d_value == nullptr)));
   e->p.kt = kt_slot(KT_STEP);
-  DISPATCH(k_step, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_prob, d_value);
+  // programmatic dependent launch (common.cuh): scheduled behind the tail of the heads kernel
+  if (e->p.NCH == 4) A5_CUDA(launch_pdl_k(k_step<4>, (unsigned)ngrid(e), WPB * 32, 0, (cudaStream_t)stream, pdl_enabled(), e->p, d_prob, d_value));
+  else A5_CUDA(launch_pdl_k(k_step<8>, (unsigned)ngrid(e), WPB * 32, 0, (cudaStream_t)stream, pdl_enabled(), e->p, d_prob, d_value));
   return A5_OK;
 }
 

@@ -38,6 +38,7 @@ struct FCBarriers {
 __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__ FCHead P, const __grid_constant__ FCHead V,
                                                          int mtiles, int n) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
   kt_begin(P.kt);
   const bool is_value = (int)blockIdx.x >= mtiles;
   const FCHead& H = is_value ? V : P;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
     const __half* a_src = H.A + (size_t)mt * H.nst * (FC_A_BYTES / 2);
     const __half* w_src = H.W;
     int st = 0, ph = 0;
+    pdl_wait();                                              // the conv layers that wrote the A operands are complete
     for (int k = 0; k < H.nst; ++k) {
       mbar_wait(&B->empty[st], ph ^ 1);
       if (elect_one()) {
@@ -267,7 +269,7 @@ int heads_forward(a5_net* net, HeadsState* h, int n, float* prob, float* value, 
   V.nst = h->nst_val; V.N = 64; V.C = 64; V.fold = 1;
   P.kt = kt_slot(KT_HEADS);
   const int mtiles = (n + 127) / 128;
-  k_tc_fc<<<2 * mtiles, FC_THREADS, h->smem, st>>>(P, V, mtiles, n);
+  A5_CUDA(launch_pdl_k(k_tc_fc, (unsigned)(2 * mtiles), FC_THREADS, (size_t)h->smem, st, pdl_enabled(), P, V, mtiles, n));
   A5_CUDA(cudaGetLastError());
   return A5_OK;
 }

@@ -94,12 +94,6 @@ __device__ __forceinline__ void dbg_mark_cta(unsigned long long* dbg, int role, 
   if (dbg && (int)blockIdx.x == cta && n < 256) dbg[role * 256 + n++] = dbg_now();
 }
 
-// Programmatic dependent launch: every conv kernel lets its successor be scheduled at once (its CTAs
-// take over SMs as this grid's CTAs exit and run their prologue -- barrier init, TMEM alloc, weight
-// prefetch -- behind this grid's tail); only the activation producer must wait for the predecessor.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ------------------------------------------------------------------ epilogue (shared by both conv kernels)
 // TMEM -> bias / ELU / hi-lo split -> HBM for the groups g_first, g_first + g_step, ... < g_end of
 // this CTA.  REMOTE: the "TMEM drained" arrival goes to the leader CTA of the pair.
@@ -805,6 +799,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __global__ void __launch_bounds__(128) k_c1_bits(const int8_t* __restrict__ planes, int n, int C, uint32_t* __restrict__ bits,
                                                  unsigned long long* kt) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();                                              // the tree pass that wrote the planes is complete
   kt_begin(kt);
   if (kt && b >= n) { __syncthreads(); return; }           // (timing on: everybody meets at the barrier below)
   if (b >= n) return;
@@ -828,6 +824,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
                                                           int n, int ntiles, uint32_t lo_add, uint32_t lo_mask,
                                                           unsigned long long* kt) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
   kt_begin(kt);
   uint8_t* a_buf = smem;                                       // 2 A tiles [kchunk 10][row 128][8]
   uint8_t* w_buf = smem + C1M_NA * C1M_ATILE;                  // [kchunk 16][hi 32 | lo 32][8]
@@ -890,6 +887,7 @@ __global__ void __launch_bounds__(C1M_THREADS) k_tc_conv1m(const uint32_t* __res
     };
     int ab = 0, aph = 0;
     Pos cur, nxt;
+    pdl_wait();                                                // k_c1_bits is complete (weights, LUT, TMEM were set up meanwhile)
     fetch(blockIdx.x, cur);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       fetch(tile + gridDim.x, nxt);
@@ -1238,11 +1236,11 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   if (parts & A5_NET_PART_FRONT) {
     const int ntiles = (int)((nrows1 + 127) / 128);
     const int grid1 = ntiles < C1M_CTAS * tc->front_sms ? ntiles : C1M_CTAS * tc->front_sms;
-    k_c1_bits<<<(n + 3) / 4, 128, 0, st>>>(planes, n, net->C, tc->c1_bits, kt_slot(KT_C1BITS));
-    A5_CUDA(cudaGetLastError());
-    k_tc_conv1m<<<grid1, C1M_THREADS, C1M_SMEM, st>>>(tc->c1_bits, tc->wpk_c1, net->bias[0], tc->act[A32], tc->plane_rows, net->S,
-                                                     ps.pitch, ps.per_board, ps.guard, n, ntiles, tc->lo_add, tc->lo_mask,
-                                                     kt_slot(KT_CONV1));
+    A5_CUDA(launch_pdl_k(k_c1_bits, (unsigned)((n + 3) / 4), 128, 0, st, tc->pdl != 0, planes, n, net->C, tc->c1_bits,
+                         kt_slot(KT_C1BITS)));
+    A5_CUDA(launch_pdl_k(k_tc_conv1m, (unsigned)grid1, C1M_THREADS, C1M_SMEM, st, tc->pdl != 0, (const uint32_t*)tc->c1_bits,
+                         (const __half*)tc->wpk_c1, (const float*)net->bias[0], tc->act[A32], tc->plane_rows, net->S, ps.pitch,
+                         ps.per_board, ps.guard, n, ntiles, tc->lo_add, tc->lo_mask, kt_slot(KT_CONV1)));
   }
   A5_CUDA(cudaGetLastError());
   TC_MARK(1);

@@ -61,6 +61,7 @@ class SearchEngine:
         # CUDA graph of one search pass (leaf evaluation + tree pass) for run_search: kernel parameters are baked
         # into it, so it is keyed on the net, its compute path and a version that set_mode / set_budget bump
         self._version = 0
+        self._mode = (bool(config.training), bool(config.random_a))
         self._graph = None
         self._graph_key = None
         self._prob = self._value = None
@@ -83,7 +84,9 @@ class SearchEngine:
 
     def set_mode(self, training: bool, random_a: bool = False):
         check(self.lib.a5_engine_set_mode(self.handle, int(training), int(random_a)))
-        self._version += 1
+        if self._mode != (bool(training), bool(random_a)):       # Player.get_action sets it on every call
+            self._mode = (bool(training), bool(random_a))
+            self._version += 1
 
     def set_budget(self, sims: int, upper: int):
         check(self.lib.a5_engine_set_budget(self.handle, int(sims), int(upper)))

@@ -515,7 +515,10 @@ def run_ours(a):
                                    "the accounted pass")
             out["roofline"] = conv_roofline(kt, S, N, pk, measured_traffic())
             out["roofline_tree"] = tree_roofline(kt, c1, c2, S, pk)
-            out["ms_per_pass_accounted"] = sum(v[0] for v in kt.values()) / 1000.0
+            # the stamps cost ~1 % (atomics, one extra CTA barrier per kernel) and the fold kernel is instrumentation only
+            out["ms_per_pass_accounted"] = sum(v[0] for k, v in kt.items() if k != "(fold)") / 1000.0
+            out["accounting_note"] = ("accounted = sum of the kernels of the instrumented replays without the stamp-folding "
+                                      "kernel; instrumented replays run ~1 % slower than the timed ones")
         else:
             flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * S * S / 121)
             tf = flop * evals / (ms / 1000) / 1e12

@@ -147,12 +147,12 @@ def test_forced_visit_picks_are_uniform(cuda_lib):
     eng.close()
 
 
-def test_self_play_records(cuda_lib):
+@pytest.mark.parametrize("S,N,sims,want", [(11, 64, 24, 40), (15, 32, 16, 16)])
+def test_self_play_records(cuda_lib, S, N, sims, want):
     """auto_play: whole games on the device (Player.run + gen_data): record invariants of
-    player.py:53-82 / main.py:86-93 / utils.py:286-296."""
+    player.py:53-82 / main.py:86-93 / utils.py:286-296, at both board sizes of BASELINE.json."""
     from alphafive_b200.engine import parse_records
     from alphafive_b200.net import DeviceNet
-    S, N, sims = 11, 64, 24
     net = DeviceNet(S, N)
     eng = _engine(S, N, sims, sims + 10, training=True, auto_play=True, seed=1)
     prob = torch.empty((N, S * S), device="cuda")
@@ -166,9 +166,9 @@ def test_self_play_records(cuda_lib):
             buf, g_ = eng.harvest()
             recs += parse_records(buf, S)
             games += g_
-            if games >= 40:
+            if games >= want:
                 break
-    assert games >= 40
+    assert games >= want
     c = eng.counters()
     assert c["overflows"] == 0 and c["records_dropped"] == 0 and c["games"] >= games
     by_game = {}
@@ -180,7 +180,7 @@ def test_self_play_records(cuda_lib):
         plies.sort(key=lambda r: r["ply"])
         L = plies[0]["game_len"]
         lens.append(L)
-        assert [r["ply"] for r in plies] == list(range(L)) and 9 <= L <= 121
+        assert [r["ply"] for r in plies] == list(range(L)) and 9 <= L <= S * S
         assert not plies[0]["board"].any() and plies[0]["last_action"] == -1
         for t in range(L - 1):
             a = plies[t + 1]["last_action"]
