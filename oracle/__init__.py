@@ -22,6 +22,12 @@ produced by running the reference's own ``utils`` / ``Player`` code here
 (``tests/golden/rules_*.npz``, ``mcts_kat_*.npz``), (ii) invariants of the
 shipped replay buffer ``data_buffer/data6960.pkl`` (``replay_sample.npz``) and
 (iii) the logged losses at ckpt-6960 for the network restatement
-(``ckpt6960.npz``).  NN outputs have no first-party golden vectors (TensorFlow
-cannot run here): for the NN, parity is pinned only through (iii).
+(``ckpt6960.npz``) and (iv) the human-vs-AI game the reference ships as
+``tmp/five_6960.gif`` (GUI.py:184-186; decoded into ``gui_game_6960.npz``): the 29
+moves its AI -- ckpt-6960 through the TensorFlow net, Player(training=False),
+542 / 642 simulations -- played are reproduced move for move by ``oracle.net``
+driving ``oracle.mcts`` (tests/test_oracle_gui_game.py), close calls included
+(198 against 193 visits).  Raw NN output vectors do not exist (TensorFlow cannot
+run here); the network restatement is pinned through (iii) and, end to end,
+through (iv).
 """

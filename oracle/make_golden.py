@@ -23,6 +23,9 @@ mcts_mix_11.npz      root / depth-1 visit counts of seeded training-mode searche
 selfplay_games_11.npz lengths / results of seeded Player.run() games (training mode)
 replay_stack.npz     utils.RandomStack driven with seeded generators: accept flags and
                      bookkeeping after every push, one get_data batch
+gui_game_6960.npz    the 58 moves of the human-vs-AI game the reference ships as tmp/five_6960.gif (written by
+                     GUI.py:184-186 with the TensorFlow net of ckpt-6960): the 29 AI moves are the one first-party
+                     known answer of network + search together
 """
 from __future__ import annotations
 
@@ -488,8 +491,55 @@ def make_replay_stack(utils):
     print("replay_stack:", sum(accepted), "of", len(games), "games accepted,", len(stack.data), "records held")
 
 
+def make_gui_game():
+    """Decode tmp/five_6960.gif.  GUI.py appends one half-size screenshot per stone (frames 1..58) after the empty
+    board, then five copies of the final position (GUI.py:176-181; self_play.py would append three, and writes
+    tmp/five.gif).  pygame.surfarray.array3d is [x][y], so frame[row = x][col = y]; a stone (i, j) is a filled circle
+    at x = (j + 1.5) * 36, y = (i + 1.5) * 36 (GUI.py draw_stone), black for the side that moved first."""
+    from PIL import Image
+    S, G = 11, 18
+    im = Image.open(os.path.join(REF, "tmp", "five_6960.gif"))
+    assert im.size == ((S + 2) * G, (S + 2) * G)
+    boards = []
+    for k in range(im.n_frames):
+        im.seek(k)
+        f = np.array(im.convert("RGB")).astype(int)
+        b = np.zeros((S, S), np.int8)
+        for i in range(S):
+            for j in range(S):
+                r, c = int((j + 1.5) * G), int((i + 1.5) * G)
+                px = f[r - 2:r + 3, c - 2:c + 3].reshape(-1, 3).mean(0)
+                b[i, j] = 1 if px.max() < 60 else (-1 if px.min() > 200 else 0)
+        boards.append(b)
+    assert not boards[0].any()
+    moves = []
+    for k in range(1, len(boards)):
+        d = np.argwhere(boards[k] != boards[k - 1])
+        if len(d) == 0:
+            continue
+        assert len(d) == 1, (k, d)
+        i, j = (int(v) for v in d[0])
+        assert boards[k - 1][i, j] == 0 and boards[k][i, j] == (1 if len(moves) % 2 == 0 else -1)
+        moves.append((i, j))
+    assert len(moves) == 58 and len(boards) == 1 + 58 + 5
+    # consistency with utils: the game is over exactly after the last move, and the mover won
+    utils = _ref()[0]
+    board = np.zeros((S, S), np.int8)
+    for t, mv in enumerate(moves):
+        board = utils.step(board, mv)
+        over, v = utils.is_game_over(board, 5)
+        assert over == (t == len(moves) - 1)
+    assert v == -1.0
+    np.savez_compressed(os.path.join(OUT, "gui_game_6960.npz"), moves=np.array(moves, np.int8), ai_first=np.int8(1),
+                        sims=np.int32(542), upper=np.int32(642), final_board=boards[-1])
+    print("gui_game_6960.npz: 58 plies, the AI (black) moved first, the human (white) completed a five on ply 58")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--gui-only" in sys.argv:
+        make_gui_game()
+        return
     if "--ckpt-only" in sys.argv:
         make_ckpt()
         return
@@ -536,6 +586,7 @@ def main():
     make_mix_stats()
     make_games()
     make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
+    make_gui_game()
 
 
 if __name__ == "__main__":

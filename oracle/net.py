@@ -16,9 +16,12 @@ is *the* CPU oracle for the network.  TF conventions reproduced:
 Variable names are the TF scope names of the shipped checkpoint
 (``bone/conv1/kernel`` ...).
 
-Parity: no TF-produced vectors exist.  Pinned only by the logged losses at
+Parity: no TF-produced output vectors exist.  Pinned (i) by the logged losses at
 ckpt-6960 (tests/test_oracle_net.py: x-entropy 2.107 / value-MSE 0.324 / entropy
-2.152 on the shipped replay sample vs 2.155 / 0.313 / 2.145 logged).
+2.152 on the shipped replay sample vs 2.155 / 0.313 / 2.145 logged) and (ii) end to
+end by the reference's own recorded game tmp/five_6960.gif (GUI.py:184-186): with
+ckpt-6960 this net, driving the search restatement, plays the AI's 29 moves exactly
+(tests/test_oracle_gui_game.py; one of them decided by 198 against 193 visits).
 """
 from __future__ import annotations
 

@@ -9,7 +9,8 @@ with zeros outside the board (odd kernels: SAME pads kh//2 on both sides); tf.la
 K [in, out]; tf.reshape of an NCHW tensor flattens as c * S*S + i * S + j; ELU alpha = 1;
 half_tanh(x) = tanh(x / 2) (network.py:163-165); prob = softmax over all S*S logits (network.py:88).
 
-Parity: unpinned by TensorFlow outputs (TF 1.x is absent and the reference ships no NN vectors).
+Parity: no TensorFlow output vectors exist (TF 1.x is absent); oracle/net.py, which this file cross-checks, is
+pinned by the logged losses and by the reference's recorded game (see its header).
 """
 from __future__ import annotations
 
