@@ -94,124 +94,83 @@ __device__ __forceinline__ void dbg_mark_cta(unsigned long long* dbg, int role, 
   if (dbg && (int)blockIdx.x == cta && n < 256) dbg[role * 256 + n++] = dbg_now();
 }
 
-// ------------------------------------------------------------------ epilogue (shared by both conv kernels)
-// TMEM -> bias / ELU / hi-lo split -> HBM for the groups g_first, g_first + g_step, ... < g_end of
-// this CTA.  REMOTE: the "TMEM drained" arrival goes to the leader CTA of the pair.
-template <int T, bool REMOTE>
-__device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, const uint32_t tmem, const float* s_bias,
-                                            const float* s_hw, const int warp, const int lane, const int cpt,
-                                            const int nbuf, const int g_first, const int g_end, const int g_step) {
-  using Cfg = TCfg<T>;
+// ------------------------------------------------------------------ epilogue (shared by the conv kernels)
+// One group: TMEM -> bias / ELU / hi-lo split -> HBM (or the fused 1x1 head conv) for the T tiles whose accumulators
+// start at TMEM column `tmem_buf`; q0 = row index (from row0) of the group's first position, rows >= qlimit are not
+// stored.  Four warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); the (M tile, 16-column)
+// units of a group are dealt round-robin to them.  All arithmetic is on values pre-scaled by ACT_SCALE.
+template <int T>
+__device__ __forceinline__ void tc_epilogue_group(const TCLayer& L, const uint32_t tmem_buf, const float* s_bias, const float* s_hw,
+                                                  const int warp, const int lane, const int cpt, const uint32_t q0,
+                                                  const uint32_t qlimit) {
   const int cout = L.cout;
-  // ===================== epilogue: TMEM -> bias / ELU / hi-lo split -> HBM =====================
-  // Four warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); the
-  // (M tile, 16-column) units of a group are dealt round-robin to them.  All arithmetic is
-  // on values pre-scaled by ACT_SCALE.
   const int quad = warp & 3;
   const int sub = (warp - 2) >> 2;
-  const int nc = cout >> 4;                               // 16-column units per tile
-  int tb = 0, tph = 0, dn = 0;
-  unsigned long long* edbg = (warp == 2 && lane == 0) ? L.dbg : nullptr;
-  const uint32_t nrows = (uint32_t)L.nrows;
   constexpr float K_ACC = OUT_SCALE * ACT_SCALE;          // accumulator -> scaled activation
   constexpr float K_L2E = 1.4426950408889634f / ACT_SCALE;
-  for (int g = g_first; g < g_end; g += g_step) {
-    mbar_wait(&B->t_full[tb], tph);
-    tc_fence_after();
-    dbg_mark(edbg, 2, dn);                               // accumulators ready
-    if (L.head_ch) {
-      // head layers: columns [0, 32) of every tile feed the fused 1x1 head conv -- a warp takes whole rows
-      // of one M tile, so the head conv sees all 32 channels of its position (cout > 32: the remaining
-      // columns are plain units, below)
-      // the four warps of a lane quadrant share the T tiles; with T = 2 two warps split the 16 policy-head
-      // outputs of a tile between them (each recomputes the 32 activations it needs)
-      constexpr int NPART = (TC_EPI_WARPS / 4) / T > 0 ? (TC_EPI_WARPS / 4) / T : 1;
-      const int part = sub / T;
-      for (int m = sub % T; m < T && (part == 0 || L.head_ch == 16); m += T * NPART) {
-        const uint32_t q = (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS + m * 128 + quad * 32 + lane;
-        const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
-        const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
-        const bool real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
-        float f[32];
+  if (L.head_ch) {
+    // head layers: columns [0, 32) of every tile feed the fused 1x1 head conv -- a warp takes whole rows
+    // of one M tile, so the head conv sees all 32 channels of its position (cout > 32: the remaining
+    // columns are plain units, below)
+    // the four warps of a lane quadrant share the T tiles; with T = 2 two warps split the 16 policy-head
+    // outputs of a tile between them (each recomputes the 32 activations it needs)
+    constexpr int NPART = (TC_EPI_WARPS / 4) / T > 0 ? (TC_EPI_WARPS / 4) / T : 1;
+    const int part = sub / T;
+    for (int m = sub % T; m < T && (part == 0 || L.head_ch == 16); m += T * NPART) {
+      const uint32_t q = q0 + (uint32_t)(m * 128 + quad * 32 + lane);
+      const uint32_t board = q / (uint32_t)L.per_board, within = q - board * (uint32_t)L.per_board;
+      const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+      const bool real = q < qlimit && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+      float f[32];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + h2 * 16);
-          tc_ld16(taddr, v);
-          if (L.fold) {
-            uint32_t v2[16];
-            tc_ld16(taddr + (uint32_t)cout, v2);
-            tc_ld_wait();
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_buf + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * cpt + h2 * 16);
+        tc_ld16(taddr, v);
+        if (L.fold) {
+          uint32_t v2[16];
+          tc_ld16(taddr + (uint32_t)cout, v2);
+          tc_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-          } else {
-            tc_ld_wait();
-          }
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tc_ld_wait();
+        }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 b4 = *(const float4*)&s_bias[h2 * 16 + 4 * e];
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = *(const float4*)&s_bias[h2 * 16 + 4 * e];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
-              const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
-              f[h2 * 16 + 4 * e + j] = x > 0.0f ? x : neg;       // ACT_SCALE * activation
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+            const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+            f[h2 * 16 + 4 * e + j] = x > 0.0f ? x : neg;       // ACT_SCALE * activation
           }
         }
-        if (real) {
-          const uint32_t cell = rr * (uint32_t)L.S + cc;
-          const uint32_t mt = board >> 7, brow = board & 127u;
-          if (L.head_ch == 16) {
-            // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8; eight outputs at a time
-            __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
+      }
+      if (real) {
+        const uint32_t cell = rr * (uint32_t)L.S + cc;
+        const uint32_t mt = board >> 7, brow = board & 127u;
+        if (L.head_ch == 16) {
+          // k = cell*16 + c -> stage = cell/2, kchunk = (cell%2)*2 + c/8; eight outputs at a time
+          __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 1)) * 2) * 4 + (cell & 1u) * 2) * 128 * 8 + brow * 8;
 #pragma unroll 1
-            for (int c8 = (NPART >= 2 ? part : 0); c8 < (NPART >= 2 ? part + 1 : 2); ++c8) {
-              float acc[8];
+          for (int c8 = (NPART >= 2 ? part : 0); c8 < (NPART >= 2 ? part + 1 : 2); ++c8) {
+            float acc[8];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) acc[c] = s_hw[32 * 16 + c8 * 8 + c];
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const float4 w0 = *(const float4*)&s_hw[k * 16 + c8 * 8];
-                const float4 w1 = *(const float4*)&s_hw[k * 16 + c8 * 8 + 4];
-                acc[0] = fmaf(f[k], w0.x, acc[0]); acc[1] = fmaf(f[k], w0.y, acc[1]);
-                acc[2] = fmaf(f[k], w0.z, acc[2]); acc[3] = fmaf(f[k], w0.w, acc[3]);
-                acc[4] = fmaf(f[k], w1.x, acc[4]); acc[5] = fmaf(f[k], w1.y, acc[5]);
-                acc[6] = fmaf(f[k], w1.z, acc[6]); acc[7] = fmaf(f[k], w1.w, acc[7]);
-              }
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
-                const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
-                const __half2 h = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                hi[e] = *(const uint32_t*)&h;
-                lo[e] = *(const uint32_t*)&l;
-              }
-              *(uint4*)(base + (size_t)c8 * 128 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *(uint4*)(base + (size_t)(4 + c8) * 128 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          } else {
-            float acc[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = s_hw[32 * 16 + c];
+            for (int c = 0; c < 8; ++c) acc[c] = s_hw[32 * 16 + c8 * 8 + c];
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              const float4 w4 = *(const float4*)&s_hw[k * 4];
-              acc[0] = fmaf(f[k], w4.x, acc[0]);
-              acc[1] = fmaf(f[k], w4.y, acc[1]);
-              acc[2] = fmaf(f[k], w4.z, acc[2]);
-              acc[3] = fmaf(f[k], w4.w, acc[3]);
+              const float4 w0 = *(const float4*)&s_hw[k * 16 + c8 * 8];
+              const float4 w1 = *(const float4*)&s_hw[k * 16 + c8 * 8 + 4];
+              acc[0] = fmaf(f[k], w0.x, acc[0]); acc[1] = fmaf(f[k], w0.y, acc[1]);
+              acc[2] = fmaf(f[k], w0.z, acc[2]); acc[3] = fmaf(f[k], w0.w, acc[3]);
+              acc[4] = fmaf(f[k], w1.x, acc[4]); acc[5] = fmaf(f[k], w1.y, acc[5]);
+              acc[6] = fmaf(f[k], w1.z, acc[6]); acc[7] = fmaf(f[k], w1.w, acc[7]);
             }
-            // k = cell*4 + c -> stage = cell/8, kchunk = (cell%8)/2, element = (cell%2)*4 + c
-            __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 3)) * 2) * 4 + ((cell & 7u) >> 1)) * 128 * 8 +
-                           brow * 8 + (cell & 1u) * 4;
-            uint32_t hi[2], lo[2];
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < 4; ++e) {
               const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
               const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
               const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
@@ -221,83 +180,132 @@ __device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, con
               hi[e] = *(const uint32_t*)&h;
               lo[e] = *(const uint32_t*)&l;
             }
-            *(uint2*)base = make_uint2(hi[0], hi[1]);
-            *(uint2*)(base + (size_t)4 * 128 * 8) = make_uint2(lo[0], lo[1]);
+            *(uint4*)(base + (size_t)c8 * 128 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *(uint4*)(base + (size_t)(4 + c8) * 128 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-        }
-      }
-    }
-    int cur_m = -1;
-    bool real = false;
-    uint32_t q = 0;
-    const int hcols = L.head_ch ? 32 : 0;                    // columns consumed by the head path above
-    const int ncp = (cout - hcols) >> 4;                     // plain 16-column units per tile
-    for (int u = sub; u < T * ncp; u += TC_EPI_WARPS / 4) {
-      const int m = u / ncp, c0 = hcols + ((u - m * ncp) << 4);
-      if (m != cur_m) {
-        cur_m = m;
-        q = (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS + m * 128 + quad * 32 + lane;      // row index from row0
-        const uint32_t within = q % (uint32_t)L.per_board;
-        const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
-        real = q < nrows && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
-      }
-      const long long row = L.row0 + q;
-      uint32_t v[16];
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * T * cpt + m * cpt + c0);
-      tc_ld16(taddr, v);
-      if (L.fold) {                                         // + a_hi * w_lo partial sums
-        uint32_t v2[16];
-        tc_ld16(taddr + (uint32_t)cout, v2);
-        tc_ld_wait();
+        } else {
+          float acc[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-      } else {
-        tc_ld_wait();
-      }
-      float f[16];
+          for (int c = 0; c < 4; ++c) acc[c] = s_hw[32 * 16 + c];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          for (int k = 0; k < 32; ++k) {
+            const float4 w4 = *(const float4*)&s_hw[k * 4];
+            acc[0] = fmaf(f[k], w4.x, acc[0]);
+            acc[1] = fmaf(f[k], w4.y, acc[1]);
+            acc[2] = fmaf(f[k], w4.z, acc[2]);
+            acc[3] = fmaf(f[k], w4.w, acc[3]);
+          }
+          // k = cell*4 + c -> stage = cell/8, kchunk = (cell%8)/2, element = (cell%2)*4 + c
+          __half* base = L.head_out + ((((size_t)mt * L.head_nst + (cell >> 3)) * 2) * 4 + ((cell & 7u) >> 1)) * 128 * 8 +
+                         brow * 8 + (cell & 1u) * 4;
+          uint32_t hi[2], lo[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
-          const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
-          f[4 * e + j] = x > 0.0f ? x : neg;
-        }
-      }
-      if (L.out || L.out2) {
-#pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
+          for (int e = 0; e < 2; ++e) {
+            const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
+            const float x0 = a0 > 0.0f ? a0 : fmaf(ex2_approx(a0 * K_L2E), ACT_SCALE, -ACT_SCALE);
+            const float x1 = a1 > 0.0f ? a1 : fmaf(ex2_approx(a1 * K_L2E), ACT_SCALE, -ACT_SCALE);
             const __half2 h = __floats2half2_rn(x0, x1);
             const float2 hf = __half22float2(h);
             const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            hi[e] = real ? *(const uint32_t*)&h : 0u;
-            lo[e] = real ? ((*(const uint32_t*)&l + L.lo_add) & L.lo_mask) : 0u;
+            hi[e] = *(const uint32_t*)&h;
+            lo[e] = *(const uint32_t*)&l;
           }
-          const bool second = L.out2 && c0 >= L.split;
-          __half* ob = second ? L.out2 : L.out;
-          const int och = L.out2 ? (second ? cout - L.split : L.split) : cout;
-          const long long chunk = ((second ? c0 - L.split : c0) >> 3) + kc;
-          __half* ph = ob + (chunk * L.plane_rows + row) * 8;
-          __half* pl = ob + (((long long)(och >> 3) + chunk) * L.plane_rows + row) * 8;
+          *(uint2*)base = make_uint2(hi[0], hi[1]);
+          *(uint2*)(base + (size_t)4 * 128 * 8) = make_uint2(lo[0], lo[1]);
+        }
+      }
+    }
+  }
+  int cur_m = -1;
+  bool real = false;
+  uint32_t q = 0;
+  const int hcols = L.head_ch ? 32 : 0;                    // columns consumed by the head path above
+  const int ncp = (cout - hcols) >> 4;                     // plain 16-column units per tile
+  for (int u = sub; u < T * ncp; u += TC_EPI_WARPS / 4) {
+    const int m = u / ncp, c0 = hcols + ((u - m * ncp) << 4);
+    if (m != cur_m) {
+      cur_m = m;
+      q = q0 + (uint32_t)(m * 128 + quad * 32 + lane);      // row index from row0
+      const uint32_t within = q % (uint32_t)L.per_board;
+      const uint32_t rr = within / (uint32_t)L.pitch, cc = within - rr * (uint32_t)L.pitch;
+      real = q < qlimit && rr < (uint32_t)L.S && cc < (uint32_t)L.S;
+    }
+    const long long row = L.row0 + q;
+    uint32_t v[16];
+    const uint32_t taddr = tmem_buf + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * cpt + c0);
+    tc_ld16(taddr, v);
+    if (L.fold) {                                         // + a_hi * w_lo partial sums
+      uint32_t v2[16];
+      tc_ld16(taddr + (uint32_t)cout, v2);
+      tc_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+    } else {
+      tc_ld_wait();
+    }
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 b4 = *(const float4*)&s_bias[c0 + 4 * e];
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = fmaf(__uint_as_float(v[4 * e + j]), K_ACC, bb[j]);
+        const float neg = fmaf(ex2_approx(x * K_L2E), ACT_SCALE, -ACT_SCALE);
+        f[4 * e + j] = x > 0.0f ? x : neg;
+      }
+    }
+    if (L.out || L.out2) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = f[kc * 8 + 2 * e], x1 = f[kc * 8 + 2 * e + 1];
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          hi[e] = real ? *(const uint32_t*)&h : 0u;
+          lo[e] = real ? ((*(const uint32_t*)&l + L.lo_add) & L.lo_mask) : 0u;
+        }
+        const bool second = L.out2 && c0 >= L.split;
+        __half* ob = second ? L.out2 : L.out;
+        const int och = L.out2 ? (second ? cout - L.split : L.split) : cout;
+        const long long chunk = ((second ? c0 - L.split : c0) >> 3) + kc;
+        __half* ph = ob + (chunk * L.plane_rows + row) * 8;
+        __half* pl = ob + (((long long)(och >> 3) + chunk) * L.plane_rows + row) * 8;
+        if (q < qlimit) {                                    // rows past the limit belong to another chunk / CTA
           *(uint4*)ph = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *(uint4*)pl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
-      if (L.out_f32 && q < nrows) {
-        constexpr float inv = 1.0f / ACT_SCALE;
-        float4* po = (float4*)(L.out_f32 + row * cout + c0);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
     }
+    if (L.out_f32 && q < qlimit) {
+      constexpr float inv = 1.0f / ACT_SCALE;
+      float4* po = (float4*)(L.out_f32 + row * cout + c0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        po[e] = real ? make_float4(f[4 * e] * inv, f[4 * e + 1] * inv, f[4 * e + 2] * inv, f[4 * e + 3] * inv)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// The groups g_first, g_first + g_step, ... < g_end of this CTA (one layer per launch).  REMOTE: the "TMEM drained"
+// arrival goes to the leader CTA of the pair.
+template <int T, bool REMOTE>
+__device__ __forceinline__ void tc_epilogue(const TCLayer& L, TCBarriers* B, const uint32_t tmem, const float* s_bias,
+                                            const float* s_hw, const int warp, const int lane, const int cpt,
+                                            const int nbuf, const int g_first, const int g_end, const int g_step) {
+  using Cfg = TCfg<T>;
+  int tb = 0, tph = 0, dn = 0;
+  unsigned long long* edbg = (warp == 2 && lane == 0) ? L.dbg : nullptr;
+  for (int g = g_first; g < g_end; g += g_step) {
+    mbar_wait(&B->t_full[tb], tph);
+    tc_fence_after();
+    dbg_mark(edbg, 2, dn);                               // accumulators ready
+    tc_epilogue_group<T>(L, tmem + (uint32_t)(tb * T * cpt), s_bias, s_hw, warp, lane, cpt,
+                         (uint32_t)(L.reverse ? g_end - 1 - g : g) * Cfg::ROWS, (uint32_t)L.nrows);
     tc_fence_before();
     __syncwarp();
     dbg_mark(edbg, 2, dn);                               // tile(s) drained
@@ -688,6 +696,343 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc
   cluster_sync_all();                                      // nobody leaves while the peer may still touch its barriers / smem
   kt_end(L.kt);
   if (L.clk && blockIdx.x == 0 && threadIdx.x == 0) { L.clk[2] = (unsigned long long)clock64(); L.clk[3] = kt_now(); }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------ the chunk-major megakernel (A5_TC_MEGA)
+// All block-conv layers of a forward in ONE persistent launch, depth first.  Every CTA owns a fixed range of whole
+// boards and walks it in chunks of CB boards (gpc groups of 256 positions); for each chunk it runs layer 0, 1, ...,
+// nl - 1 before it moves to the next chunk.  Boards are independent and the position space puts zero rows between
+// them, so everything a CTA reads in layer l + 1 was written by ITSELF in layer l: there is no dependency between
+// CTAs, no grid barrier and no launch boundary between the layers -- only program order inside the CTA (the
+// epilogue publishes the units it has stored, the activation producer waits for the unit that covers its slab and
+// its halo).  A chunk of 7 boards x 148 CTAs keeps a layer's output (<= 77 MB) in the 126 MB L2 until the next layer
+// reads it, the slab / weight / TMEM pipelines never drain between layers, and the last-wave quantisation is per
+// forward (28 boards = 31.5 tiles per CTA) instead of per layer.  Weights always stream through a ring of three-tap
+// stages.
+constexpr int TCM_MAXL = 8;
+struct TCMega {
+  TCLayer L[TCM_MAXL];
+  int dep_src[TCM_MAXL], dep_src2[TCM_MAXL], dep_res[TCM_MAXL];   // layer of this launch that writes the tensor, or -1
+  int nl;
+  int B, n_hi;             // CTAs [0, n_hi) own B + 1 boards, the others B
+  int CB, nchunks, gpc;    // boards per chunk; chunks per CTA and groups per chunk (the same for every CTA)
+  unsigned long long* kt;
+  unsigned long long* dbg; // tooling: [nchunks * nl + 1][2] = {%globaltimer, clock64} when CTA 0's issuer starts a (chunk, layer)
+};
+constexpr int TCM_MISC = TCM_MAXL * 128 * 4 + 256 + 2 * (32 * 16 + 16) * 4 + 128 + 64;
+// weight ring: a stage holds up to three (slab, tap) blocks -- one full / empty handshake and one commit per three
+// taps keeps the two issuing threads ahead of the tensor pipe also for the N <= 64 layers (a handshake per tap does
+// not: ~200 cycles of waits, elect and commits per 4 MMAs)
+constexpr int TCM_TPS = 3;
+constexpr int TCM_WST = TCM_TPS * TC2_WSTAGE_MAX;         // 24 KB
+constexpr int TCM_NWS = 4;
+constexpr int TCM_WBYTES = TCM_NWS * TCM_WST;
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// rows of chunk k of this CTA: first row index (from row0) and the first row past its boards
+__device__ __forceinline__ void tcm_chunk(const TCMega& P, int cta, int k, uint32_t& q0, uint32_t& qlim) {
+  const int per_board = P.L[0].per_board;
+  const int first = cta * P.B + min(cta, P.n_hi), nb = P.B + (cta < P.n_hi ? 1 : 0);
+  const int b0 = min(k * P.CB, nb), b1 = min((k + 1) * P.CB, nb);
+  const uint32_t nrows = (uint32_t)P.L[0].nrows;
+  q0 = min((uint32_t)(first + b0) * (uint32_t)per_board, nrows);
+  qlim = min((uint32_t)(first + b1) * (uint32_t)per_board, nrows);
+}
+
+template <int HALO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) k_tc_mega(const __grid_constant__ TCMega P) {
+  constexpr int T = 2;
+  using Cfg = TCfgH<T, HALO>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NSB = (TC2_SMEM_LIMIT - TCM_MISC - TCM_WBYTES) / Cfg::SLAB > 4 ? 4 : (TC2_SMEM_LIMIT - TCM_MISC - TCM_WBYTES) / Cfg::SLAB;
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + NSB * Cfg::SLAB;
+  float* s_bias = (float*)(w_buf + TCM_WBYTES);                              // [nl][128]
+  TCBarriers* B = (TCBarriers*)(s_bias + TCM_MAXL * 128);
+  float* s_hw = (float*)((uint8_t*)B + 256);                                 // [2][32 * 16 + 16]
+  volatile int* s_done = (volatile int*)(s_hw + 2 * (32 * 16 + 16));         // [16] units stored, per epilogue warp
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cta = (int)blockIdx.x;
+  const int nl = P.nl, gpc = P.gpc, nchunks = P.nchunks;
+
+  pdl_launch_dependents();
+  kt_begin(P.kt);
+  for (int i = threadIdx.x; i < nl * 128; i += TC2_THREADS) {
+    const int li = i >> 7, c = i & 127;
+    s_bias[i] = c < P.L[li].cout ? P.L[li].bias[c] * ACT_SCALE : 0.0f;
+  }
+  {
+    int hs = 0;
+    for (int li = 0; li < nl; ++li)
+      if (P.L[li].head_ch) {
+        float* hw = s_hw + hs * (32 * 16 + 16);
+        for (int i = threadIdx.x; i < 32 * P.L[li].head_ch; i += TC2_THREADS) hw[i] = P.L[li].head_w[i];
+        if (threadIdx.x < P.L[li].head_ch) hw[32 * 16 + threadIdx.x] = P.L[li].head_b[threadIdx.x] * ACT_SCALE;
+        ++hs;
+      }
+  }
+  if (threadIdx.x < 16) s_done[threadIdx.x] = 0;
+  if (warp == 0 && lane == 0) {
+    const uint32_t full_count = rank == 0 ? 2u : 1u;       // leader: own producer + the peer's relay
+    for (int i = 0; i < 4; ++i) { mbar_init(&B->a_full[i], full_count); mbar_init(&B->a_empty[i], 2); }
+    for (int i = 0; i < TCM_NWS; ++i) { mbar_init(&B->w_full[i], full_count); mbar_init(&B->w_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&B->t_full[i], 2); mbar_init(&B->t_empty[i], 2 * TC_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = B->tmem_base;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    int ab = 0, aph = 0, seen = 0;
+    pdl_wait();                                              // conv1 (the layer before this launch) is complete
+    for (int k = 0; k < nchunks; ++k) {
+      uint32_t qc, qlim;
+      tcm_chunk(P, cta, k, qc, qlim);
+      for (int li = 0; li < nl; ++li) {
+        const TCLayer& L = P.L[li];
+        const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
+        const int m0s = L.src_ch / TC_KS;
+        for (int g = 0; g < gpc; ++g) {
+          const long long r0 = L.row0 + (long long)qc + (long long)g * Cfg::ROWS - HALO;
+          SlabSeq seq(main_slabs, res_slabs, L.src2 ? 1 : 0);
+          for (int s = 0; s < main_slabs + res_slabs; ++s) {
+            int sidx;
+            const bool is_res = seq.next(sidx);
+            const SlabInfo si = slab_info(L, is_res, sidx);
+            // the unit (of this CTA, this chunk) that wrote the last rows this slab reads: group g + 1 holds the halo
+            const int dl = is_res ? P.dep_res[li] : (sidx < m0s ? P.dep_src[li] : P.dep_src2[li]);
+            if (dl >= 0) {
+              const int need = (k * nl + dl) * gpc + min(g + 1, gpc - 1) + 1;
+              for (uint32_t spin = 0; seen < need; ++spin) {
+                int v = lane < TC_EPI_WARPS ? s_done[lane] : 0x7fffffff;
+                seen = __reduce_min_sync(FULL, v);
+                if (spin > (1u << 26)) __trap();             // a lost unit must fail loudly, not hang the GPU
+              }
+              fence_proxy_async_all();                       // the epilogue's generic-proxy stores before the bulk reads
+            }
+            mbar_wait(&B->a_empty[ab], aph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&B->a_full[ab], Cfg::SLAB);
+              uint8_t* dst = a_buf + ab * Cfg::SLAB;
+#pragma unroll
+              for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                for (int j = 0; j < TC_KS / 8; ++j) {
+                  const __half* p = si.X + ((long long)(hl * (si.xch / 8) + si.kc0 + j) * L.plane_rows + r0) * 8;
+                  bulk_g2s(dst + (hl * (TC_KS / 8) + j) * Cfg::PLANE, p, Cfg::PLANE, &B->a_full[ab]);
+                }
+            }
+            __syncwarp();
+            if (++ab == NSB) { ab = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == TC_W_WARP) {
+    // ===================== W producer: every (slab, tap) stage of every group through the ring =====================
+    int ws = 0, wph = 0;
+    for (int k = 0; k < nchunks; ++k)
+      for (int li = 0; li < nl; ++li) {
+        const TCLayer& L = P.L[li];
+        const uint8_t* wsrc0 = (const uint8_t*)L.wpk;
+        const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
+        for (int g = 0; g < gpc; ++g) {
+          SlabSeq seq(main_slabs, res_slabs, L.src2 ? 1 : 0);
+          for (int s = 0; s < main_slabs + res_slabs; ++s) {
+            int sidx;
+            const bool is_res = seq.next(sidx);
+            const SlabInfo si = slab_info(L, is_res, sidx);
+            for (int t0 = 0; t0 < si.ntap; t0 += TCM_TPS) {
+              const int nt = min(TCM_TPS, si.ntap - t0);
+              mbar_wait(&B->w_empty[ws], wph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&B->w_full[ws], (uint32_t)nt * si.sbytes);
+                for (int j = 0; j < nt; ++j) {
+                  const uint32_t off = si.wbase + (uint32_t)(si.wstage + t0 + j) * si.sbytes;
+                  bulk_g2s(w_buf + ws * TCM_WST + j * si.sbytes, wsrc0 + 2u * (size_t)off + (size_t)rank * si.sbytes, si.sbytes,
+                           &B->w_full[ws]);
+                }
+              }
+              __syncwarp();
+              if (++ws == TCM_NWS) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+      }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer relay =====================
+    int ab = 0, aph = 0, ws = 0, wph = 0;
+    for (int k = 0; k < nchunks; ++k)
+      for (int li = 0; li < nl; ++li) {
+        const TCLayer& L = P.L[li];
+        const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
+        for (int g = 0; g < gpc; ++g) {
+          SlabSeq seq(main_slabs, res_slabs, L.src2 ? 1 : 0);
+          for (int s = 0; s < main_slabs + res_slabs; ++s) {
+            int sidx;
+            const int ntap = seq.next(sidx) ? 1 : L.ntaps;
+            mbar_wait(&B->a_full[ab], aph);
+            if (lane == 0) mbar_arrive_remote(&B->a_full[ab], 0);
+            __syncwarp();
+            if (++ab == NSB) { ab = 0; aph ^= 1; }
+            for (int t0 = 0; t0 < ntap; t0 += TCM_TPS) {
+              mbar_wait(&B->w_full[ws], wph);
+              if (lane == 0) mbar_arrive_remote(&B->w_full[ws], 0);
+              __syncwarp();
+              if (++ws == TCM_NWS) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+      }
+  } else if ((warp == 1 || warp == TC2_MMA_WARP1) && rank == 0) {
+    // ===================== MMA issuers (leader) =====================
+    const int m0 = (warp == 1) ? 0 : T / 2;
+    constexpr uint32_t A_TILE = 128u * 16u / 16u;
+    constexpr uint32_t A_K16 = 2u * Cfg::PLANE / 16u;
+    constexpr uint32_t A_LO = (TC_KS / 8) * Cfg::PLANE / 16u;
+    const uint64_t ad64 = smem_desc(smem_u32(a_buf) + (uint32_t)HALO * 16u, Cfg::PLANE, 128);
+    const uint32_t a_hi = (uint32_t)(ad64 >> 32), b_hi = (uint32_t)(smem_desc(0, 0, 128) >> 32);
+    const uint32_t ad_base = (uint32_t)ad64 + (uint32_t)m0 * A_TILE;
+    const uint32_t w_addr16 = (smem_u32(w_buf) & 0x3FFFFu) >> 4;
+    constexpr uint32_t w_step = (uint32_t)(TCM_WST / 16);
+    int ab = 0, aph = 0, ws = 0, wph = 0, tb = 0, tph = 0;
+    for (int k = 0; k < nchunks; ++k)
+      for (int li = 0; li < nl; ++li) {
+        const TCLayer& L = P.L[li];
+        const bool fold = L.fold != 0;
+        const int cpt = fold ? 2 * L.cout : L.cout;
+        const int main_slabs = L.src_ch / TC_KS + (L.src2 ? L.src2_ch / TC_KS : 0), res_slabs = L.res ? L.res_ch / TC_KS : 0;
+        const int lead = L.src2 ? 1 : 0;
+        int sh[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) sh[t] = L.shifts[t];
+        if (P.dbg && cta == 0 && warp == 1 && lane == 0) {
+          P.dbg[2 * (k * nl + li)] = kt_now();
+          P.dbg[2 * (k * nl + li) + 1] = (unsigned long long)clock64();
+        }
+        for (int g = 0; g < gpc; ++g) {
+          mbar_wait_cluster(&B->t_empty[tb], tph ^ 1);
+          tc_fence_after();
+          const uint32_t d0 = tmem + (uint32_t)(tb * 256 + m0 * cpt);
+          SlabSeq seq(main_slabs, res_slabs, lead);
+          for (int s = 0; s < main_slabs + res_slabs; ++s) {
+            int sidx;
+            const bool is_res = seq.next(sidx);
+            const SlabInfo si = slab_info(L, is_res, sidx);
+            const int ntap = si.ntap;
+            const uint32_t rows = fold ? (uint32_t)(si.n + si.n / 2) : (uint32_t)si.n;
+            const uint32_t w_k16 = 2u * rows, w_s16 = fold ? (uint32_t)si.n : (uint32_t)(si.n / 2);
+            const uint32_t idesc = instr_desc(256, si.n), idesc2 = instr_desc(256, 2 * si.n);
+            const uint32_t bd_lbo = rows << 16;
+            const uint32_t dcol = d0 + (uint32_t)si.col0;
+            mbar_wait_cluster(&B->a_full[ab], aph);
+            tc_fence_after();
+            const uint32_t ad_slab = ad_base + (uint32_t)(ab * (Cfg::SLAB / 16));
+            const uint32_t first0 = lead ? (is_res ? (uint32_t)sidx : 1u) : ((uint32_t)si.wstage | (is_res ? 1u : 0u));
+            const uint32_t sb16 = si.sbytes / 16u;
+            const bool last_slab = s == main_slabs + res_slabs - 1;
+#pragma unroll
+            for (int t0 = 0; t0 < 9; t0 += TCM_TPS) {
+              if (t0 < ntap) {
+                mbar_wait_cluster(&B->w_full[ws], wph);
+                tc_fence_after();
+                const uint32_t bst = (w_addr16 + (uint32_t)ws * w_step) | bd_lbo;
+                const bool last_stage = t0 + TCM_TPS >= ntap;
+                if (elect_one()) {
+#pragma unroll
+                  for (int j = 0; j < TCM_TPS; ++j) {
+                    const int t = t0 + j;
+                    if (t < ntap) {
+                      const uint32_t ad0 = ad_slab + (uint32_t)(is_res ? 0 : sh[t]);
+                      const uint32_t bd0 = bst + (uint32_t)j * sb16;
+                      const uint32_t first = first0 | (uint32_t)t;
+                      if (fold) {
+#pragma unroll
+                        for (int kk = 0; kk < TC_KS / 16; ++kk)
+                          tc_mma2s(dcol, ad0 + kk * A_K16, a_hi, bd0 + kk * w_k16, b_hi, idesc2, (first | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < TC_KS / 16; ++kk)
+                          tc_mma2s(dcol, ad0 + kk * A_K16 + A_LO, a_hi, bd0 + kk * w_k16 + w_s16, b_hi, idesc, 1u);
+                      } else {
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+                          for (int kk = 0; kk < TC_KS / 16; ++kk)
+                            tc_mma2s(dcol, ad0 + kk * A_K16 + (pass == 1 ? A_LO : 0), a_hi,
+                                     bd0 + kk * w_k16 + (pass == 2 ? w_s16 : 0), b_hi, idesc, (first | pass | kk) != 0);
+                      }
+                    }
+                  }
+                  tc_commit2(&B->w_empty[ws]);
+                  if (last_stage) tc_commit2(&B->a_empty[ab]);
+                  if (last_stage && last_slab) tc_commit2(&B->t_full[tb]);
+                }
+                __syncwarp();
+                if (++ws == TCM_NWS) { ws = 0; wph ^= 1; }
+              }
+            }
+            if (++ab == NSB) { ab = 0; aph ^= 1; }
+          }
+          if (++tb == 2) { tb = 0; tph ^= 1; }
+        }
+      }
+  } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
+    // ===================== epilogue =====================
+    int tb = 0, tph = 0, unit = 0;
+    for (int k = 0; k < nchunks; ++k) {
+      uint32_t qc, qlim;
+      tcm_chunk(P, cta, k, qc, qlim);
+      int hs = 0;
+      for (int li = 0; li < nl; ++li) {
+        const TCLayer& L = P.L[li];
+        const int cpt = L.fold ? 2 * L.cout : L.cout;
+        const float* hw = s_hw + hs * (32 * 16 + 16);
+        if (L.head_ch) ++hs;
+        for (int g = 0; g < gpc; ++g) {
+          mbar_wait(&B->t_full[tb], tph);
+          tc_fence_after();
+          tc_epilogue_group<T>(L, tmem + (uint32_t)(tb * 256), s_bias + li * 128, hw, warp, lane, cpt,
+                               qc + (uint32_t)(g * Cfg::ROWS), qlim);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank != 0) mbar_arrive_remote(&B->t_empty[tb], 0);
+            else mbar_arrive(&B->t_empty[tb]);
+          }
+          // publish: this warp's stores of the unit are visible to the bulk-copy (async) proxy of this SM
+          __threadfence();
+          fence_proxy_async_all();
+          __syncwarp();
+          ++unit;
+          if (lane == 0) s_done[warp - 2] = unit;
+          if (++tb == 2) { tb = 0; tph ^= 1; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  kt_end(P.kt);
+  if (P.dbg && cta == 0 && threadIdx.x == 0) {
+    P.dbg[2 * (nchunks * nl)] = kt_now();
+    P.dbg[2 * (nchunks * nl) + 1] = (unsigned long long)clock64();
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -1095,6 +1440,7 @@ struct a5_tc_state {
   // with no measurable change of the output error (profiles/r02_lo_bits.txt).  A5_TC_LO_DROP=0..8 overrides.
   int lo_drop = 4;
   uint32_t lo_add = 0, lo_mask = 0xFFFFFFFFu;   // both fp16 lanes of a packed pair
+  int mega = 0;                 // A5_TC_MEGA=1: all block convs as one chunk-major launch (k_tc_mega)
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
   int fold = 1;
@@ -1125,7 +1471,9 @@ static long long tc_plane_rows(const a5_net* net) {
   PosSpace ps(net->S);
   long long valid = (long long)net->max_batch * ps.per_board;
   long long padded = (valid + 1023) / 1024 * 1024;       // whole pair-groups for every T
-  return ps.guard + padded + ps.guard + TC_HALO;
+  // + one chunk of slack: the megakernel's CTAs all run the same number of groups, the surplus ones read (never
+  // write) rows past the last board
+  return ps.guard + padded + ps.guard + TC_HALO + 1024 + 64;
 }
 
 int tc_alloc(a5_net* net) {
@@ -1153,6 +1501,8 @@ int tc_alloc(a5_net* net) {
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   A5_CUDA(cudaFuncSetAttribute(k_tc_conv2<2, true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_mega<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
+  A5_CUDA(cudaFuncSetAttribute(k_tc_mega<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT));
   // tuning knobs: M tiles per group for Cout = 128 / 64, and N-folding of the hi/lo weight halves
   const char* ev;
   tc->fold = ((ev = getenv("A5_TC_FOLD")) && atoi(ev) == 0) ? 0 : 1;
@@ -1161,6 +1511,7 @@ int tc_alloc(a5_net* net) {
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge2 = ((ev = getenv("A5_TC_MERGE2")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
+  tc->mega = ((ev = getenv("A5_TC_MEGA")) && atoi(ev) != 0) ? 1 : 0;
   if ((ev = getenv("A5_TC_LO_DROP")) && atoi(ev) >= 0 && atoi(ev) <= 8) tc->lo_drop = atoi(ev);
   {
     const uint32_t d = (uint32_t)tc->lo_drop, r = d ? (1u << (d - 1)) : 0u, m = ~((1u << d) - 1u) & 0xFFFFu;
@@ -1246,6 +1597,9 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
   TC_MARK(1);
   const long long nrows = (long long)n * ps.per_board;
   int nexec = 0;                                   // conv layers launched so far (alternating walk direction)
+  const bool mega = tc->mega && tc->merge && tc->merge2 && !g_tc_dbg && !g_tc_events && !g_tc_keep_head_acts;
+  TCMega M;
+  if (mega) memset(&M, 0, sizeof(M));
   for (int l = 1; l <= 10 && (parts & A5_NET_PART_BODY); ++l) {
     TcLayerDef D = kTcLayers[l];
     TCLayer L;
@@ -1287,6 +1641,12 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     L.plane_rows = tc->plane_rows; L.row0 = ps.guard; L.nrows = nrows;
     L.lo_add = tc->lo_add; L.lo_mask = tc->lo_mask;
     L.S = net->S; L.pitch = ps.pitch; L.per_board = ps.per_board;
+    if (mega) {
+      L.wpk = merged ? tc->wpk2_m : (merged2 ? tc->wpk2_m2 : tc->wpk2[l]);
+      L.reverse = 0; L.kt = nullptr; L.clk = nullptr;
+      M.L[M.nl++] = L;
+      continue;
+    }
     {
       // CTA pairs: T = 2 tiles per CTA, 4 per weight stage; TMEM double-buffers for every layer
       constexpr int T = 2;
@@ -1317,6 +1677,36 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     }
     A5_CUDA(cudaGetLastError());
     TC_MARK(1 + l);
+  }
+  if (mega && (parts & A5_NET_PART_BODY)) {
+    // launch order: b1c1 b1c2 b2c1 b2c2 (b3c1+b4c1) (b3c2+b4c2) b5c1 b5c2; who wrote each layer's inputs
+    static const int dsrc[8] = {-1, 0, 1, 2, 3, 4, 5, 6}, dsrc2[8] = {-1, -1, -1, -1, -1, 4, -1, -1}, dres[8] = {-1, -1, -1, 1, -1, 3, -1, 5};
+    for (int i = 0; i < 8; ++i) { M.dep_src[i] = dsrc[i]; M.dep_src2[i] = dsrc2[i]; M.dep_res[i] = dres[i]; }
+    int grid = tc->num_sms & ~1;
+    if (n < grid) grid = (n + 1) & ~1;
+    M.B = n / grid; M.n_hi = n % grid;
+    const int bmax = M.B + (M.n_hi ? 1 : 0);
+    // boards per chunk: every CTA runs nchunks x gpc groups whatever it owns, so pick the chunk (<= 2048 positions:
+    // a layer's output of 148 such chunks must stay in L2) that wastes the fewest groups; ties -> the smaller chunk
+    int cb = 1, best = 1 << 30;
+    for (int c = 1; c <= bmax && (c == 1 || c * ps.per_board <= 2048); ++c) {
+      if ((c * ps.per_board + 255) / 256 < 3 && c < bmax) continue;      // < 3 groups per layer: the pipelines drain at every layer
+      const int cost = ((bmax + c - 1) / c) * ((c * ps.per_board + 255) / 256);
+      if (cost < best) { best = cost; cb = c; }
+    }
+    { const char* ev = getenv("A5_TC_MEGA_CB"); if (ev && atoi(ev) >= 1 && atoi(ev) <= bmax) cb = atoi(ev); }
+    M.CB = cb;
+    M.gpc = (cb * ps.per_board + 255) / 256;
+    M.nchunks = (bmax + cb - 1) / cb;
+    M.dbg = g_tc_clk;                                  // a5__debug_clk: in mega mode [(nchunks * nl + 1)][2]
+    M.kt = kt_slot(KT_CONV0);
+    const bool h16 = ps.pitch + 1 <= 16;
+    const int slab = h16 ? TCfgH<2, 16>::SLAB : TCfgH<2, 24>::SLAB;
+    int nsb = (TC2_SMEM_LIMIT - TCM_MISC - TCM_WBYTES) / slab;
+    if (nsb > 4) nsb = 4;
+    const size_t smem = (size_t)nsb * slab + TCM_WBYTES + TCM_MISC;
+    if (h16) A5_CUDA(launch_pdl_k(k_tc_mega<16>, (unsigned)grid, TC2_THREADS, smem, st, tc->pdl != 0, M));
+    else A5_CUDA(launch_pdl_k(k_tc_mega<24>, (unsigned)grid, TC2_THREADS, smem, st, tc->pdl != 0, M));
   }
   int rc = (parts & A5_NET_PART_HEADS) ? heads_forward(net, tc->heads, n, prob, value, st) : A5_OK;
   TC_MARK(12);

@@ -99,3 +99,23 @@ def test_eval_is_the_reference_pv_fn_seam(cuda_lib):
     x = np.zeros((1, 3, 11, 11), np.float32)
     p, v = net.eval(x)
     assert p.shape == (1, 121) and v.shape == (1,) and p.dtype == np.float32 and v.dtype == np.float32
+
+
+@pytest.mark.parametrize("S,n", [(11, 1), (11, 300), (11, 1500), (15, 77), (9, 40)])
+def test_chunk_major_megakernel_is_bitwise_identical(cuda_lib, S, n, monkeypatch):
+    """A5_TC_MEGA=1 runs the eight block-conv launches as one depth-first persistent kernel (every CTA walks its own
+    boards chunk by chunk through all layers).  Same MMAs in the same order per position, so the outputs
+    are bit for bit those of the layer-per-launch path, ragged batches and all board sizes included."""
+    from alphafive_b200.net import DeviceNet, glorot_init
+    rng = np.random.default_rng(n)
+    planes = torch.from_numpy((rng.random((n, 3, S, S)) < 0.25).astype(np.int8)).cuda()
+    w = glorot_init(S, seed=2)
+    monkeypatch.setenv("A5_TC_MEGA", "0")
+    a = DeviceNet(S, n, w)
+    monkeypatch.setenv("A5_TC_MEGA", "1")
+    b = DeviceNet(S, n, w)
+    pa, va = a.forward(planes)
+    pb, vb = b.forward(planes)
+    pb2, vb2 = b.forward(planes)
+    assert torch.equal(pa, pb) and torch.equal(va, vb) and torch.equal(pb, pb2) and torch.equal(vb, vb2)
+    a.close(); b.close()

@@ -1,14 +1,15 @@
 """Per-layer duration, SM clock and CTA-0 cycles of the block-conv launches inside a continuous stream of forwards
 (GPU tooling; a5__debug_clk stamps clock64 + %globaltimer at start / end of CTA 0; the time of a launch includes its
-programmatic-dependent-launch wait for the predecessor).  python tools/layer_clocks.py [reps]"""
+programmatic-dependent-launch wait for the predecessor).  python tools/layer_clocks.py [reps] [boards per forward]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from alphafive_b200 import _lib
 from alphafive_b200._lib import check, ptr, stream_ptr
 from alphafive_b200.net import DeviceNet, glorot_init
-S, n = 11, 4096
+S = 11
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 lib = _lib.load()
 lib.a5__debug_clk.argtypes = [C.c_void_p]; lib.a5__debug_clk.restype = C.c_int
 net = DeviceNet(S, n, glorot_init(S, 0), mode=_lib.NET_TC)
@@ -28,4 +29,4 @@ names = ["b1c1", "b1c2", "b2c1", "b2c2", "mc1", "mc2", "b5c1", "b5c2"]
 k = len(range(reps // 2, reps, 10))
 for i, nm in enumerate(names):
     print(f"{nm:5s} {acc[i,1]/k/1e3:8.1f} us  {acc[i,0]/acc[i,1]*1e3:7.1f} MHz  {acc[i,0]/k:10.0f} cycles")
-print(f"sum   {acc[:,1].sum()/k/1e3:8.1f} us")
+print(f"sum   {acc[:,1].sum()/k/1e3:8.1f} us for {n} boards  ({acc[:,1].sum()/k/1e3*4096/n:8.1f} us per 4096)  mean clock {acc[:,0].sum()/acc[:,1].sum()*1e3:7.1f} MHz")
