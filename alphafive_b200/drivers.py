@@ -193,7 +193,7 @@ class Arena:
                 eng = self.engines[k]
                 eng.set_roots(boards, last, act_k.to(torch.uint8), clear if first[k] else None)
                 first[k] = False
-                eng.run_search(net=self.nets[k], check_every=self.check_every)
+                eng.run_search(net=self.nets[k], check_every=self.check_every, active=act_k)
                 _, a = eng.finish_move()
                 action = torch.where(act_k, a, action)
             nxt = rules.step(boards, action.clamp(min=0))

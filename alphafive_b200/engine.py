@@ -171,9 +171,12 @@ class SearchEngine:
         return buf[:cnt.value], games.value
 
     # -- convenience: run until every game's budget is spent (auto_play = 0) ------
-    def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None):
+    def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None, active=None):
         """Drive step/forward until no game is busy.  ``net`` is a DeviceNet (on-device
-        leaf evaluation, ``net_mode`` overrides its compute path); ``pv_fn`` is a reference-style host callable."""
+        leaf evaluation, ``net_mode`` overrides its compute path); ``pv_fn`` is a reference-style host callable.
+        ``active`` (bool / uint8 [N] device tensor, the mask given to set_roots): when fewer than ~3/4 of the slots
+        search -- the arena, where each player only moves in half of the games (choose_best_player.py:48-52) -- only
+        their leaves go through the network (gather planes -> forward -> scatter prob / value)."""
         assert (net is None) != (pv_fn is None)
         if self._prob is None:
             self._prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
@@ -203,6 +206,23 @@ class SearchEngine:
                 # bounds the first burst when the budgets are not known to be small)
                 left = max(1, int(self.sims_left().max().item()))
                 it += left
+                idx = None
+                if active is not None:
+                    idx = torch.nonzero(torch.as_tensor(active, device=self.device).reshape(-1)).reshape(-1)
+                    if idx.numel() == 0 or 4 * idx.numel() > 3 * self.N:
+                        idx = None
+                if idx is not None:
+                    planes = self.planes()
+                    pc = torch.empty((idx.numel(), self.C), dtype=torch.float32, device=self.device)
+                    vc = torch.empty((idx.numel(),), dtype=torch.float32, device=self.device)
+                    for _ in range(left):
+                        net.forward(planes.index_select(0, idx), pc, vc, net_mode)
+                        prob.index_copy_(0, idx, pc)
+                        value.index_copy_(0, idx, vc)
+                        self.step(prob, value)
+                    if self.busy() == 0:
+                        break
+                    continue
                 key = (id(net), net_mode, self._version)
                 if self.use_graph and left >= 4 and self._graph_key != key:
                     # one eager pass (counts), then capture the pass; replays keep the launch gaps off the GPU
