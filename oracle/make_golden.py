@@ -23,6 +23,7 @@ mcts_mix_11.npz      root / depth-1 visit counts of seeded training-mode searche
 selfplay_games_11.npz lengths / results of seeded Player.run() games (training mode)
 replay_stack.npz     utils.RandomStack driven with seeded generators: accept flags and
                      bookkeeping after every push, one get_data batch
+buffer_games_6960.npz lengths / results of the 470 games of the shipped replay buffer
 gui_game_6960.npz    the 58 moves of the human-vs-AI game the reference ships as tmp/five_6960.gif (written by
                      GUI.py:184-186 with the TensorFlow net of ckpt-6960): the 29 AI moves are the one first-party
                      known answer of network + search together
@@ -491,6 +492,17 @@ def make_replay_stack(utils):
     print("replay_stack:", sum(accepted), "of", len(games), "games accepted,", len(stack.data), "records held")
 
 
+def make_buffer_games():
+    """Lengths and results of the 470 games in the shipped replay buffer (data_buffer/data_len6960.pkl,
+    result6960.pkl): what utils.RandomStack (utils.py:64-116) had kept of the training-mode self-play around
+    step 6960 -- a distributional pin for self-play with the trained net."""
+    lens = np.array(pickle.load(open(os.path.join(REF, "data_buffer", "data_len6960.pkl"), "rb")), np.int32)
+    res = np.array(pickle.load(open(os.path.join(REF, "data_buffer", "result6960.pkl"), "rb")), np.int8)
+    assert len(lens) == len(res) == 470
+    np.savez_compressed(os.path.join(OUT, "buffer_games_6960.npz"), lens=lens, results=res)
+    print("buffer_games_6960.npz: %d games, mean length %.2f, black %d white %d" % (len(lens), lens.mean(), (res == 1).sum(), (res == -1).sum()))
+
+
 def make_gui_game():
     """Decode tmp/five_6960.gif.  GUI.py appends one half-size screenshot per stone (frames 1..58) after the empty
     board, then five copies of the final position (GUI.py:176-181; self_play.py would append three, and writes
@@ -540,6 +552,9 @@ def main():
     if "--gui-only" in sys.argv:
         make_gui_game()
         return
+    if "--buffer-games-only" in sys.argv:
+        make_buffer_games()
+        return
     if "--ckpt-only" in sys.argv:
         make_ckpt()
         return
@@ -587,6 +602,7 @@ def main():
     make_games()
     make_games(games=200, sims=300, upper=380, name="selfplay_games_11_s300.npz")
     make_gui_game()
+    make_buffer_games()
 
 
 if __name__ == "__main__":

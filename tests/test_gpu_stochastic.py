@@ -223,3 +223,57 @@ def test_whole_game_distribution(cuda_lib, fixture):
     se = np.sqrt(ent.var(0) / N + ref_ent.var(0) / len(ref_ent))
     assert (np.abs(ent.mean(0) - ref_ent.mean(0)) < 4.0 * se + 2e-3).all(), (ent.mean(0), ref_ent.mean(0))
     eng.close()
+
+
+def test_self_play_with_the_trained_net_fills_the_buffer_like_the_reference(cuda_lib):
+    """First-party distributional pin of training-mode self-play with the real network: the reference ships the
+    replay buffer its five workers had filled around step 6960 (470 games after utils.RandomStack's short-game
+    rejection, colour re-balancing duplicates and FIFO eviction, utils.py:64-116).  Device self-play with ckpt-6960
+    at config.py's 542 / 642 simulations, pushed through the same bookkeeping, must leave a buffer of the same
+    character: mean game length 25.5 (sd 8.5), 53 % black wins.  (The shipped games come from the checkpoints
+    *before* 6960, so the match is statistical and the bounds are ~3 standard errors of a 470-game buffer plus that
+    drift; measured: 24.5 +- 0.24 plies, 56 % black.)"""
+    import random
+    from alphafive_b200.engine import parse_records
+    from alphafive_b200.net import DeviceNet
+    from alphafive_b200.selfplay import SelfPlay
+    g = golden("buffer_games_6960.npz")
+    z = golden("ckpt6960.npz")
+    N, sims, upper = 1024, 542, 642
+    net = DeviceNet(11, N, {k.replace("__", "/"): z[k] for k in z.files})
+    sp = SelfPlay(None, n_games=N, net=net, training=True, seed=11, board_size=11, simulation_per_step=sims,
+                  upper_simulation_per_step=upper)
+    lens, res = [], []
+    while len(lens) < 1500:
+        sp.run_passes(sims * 4)
+        seen = set()
+        for r in parse_records(sp.harvest()[0], 11):
+            if (r["game_id"], r["game_serial"]) not in seen:
+                seen.add((r["game_id"], r["game_serial"]))
+                lens.append(int(r["game_len"])); res.append(int(r["result"]))
+    assert sp.engine.counters()["overflows"] == 0
+    means, blacks = [], []
+    for seed in range(8):                                  # the bookkeeping of utils.py:64-116 on (length, result)
+        rnd, L, R, bw, ww, total = random.Random(seed), [], [], 0, 0, 0
+        for l, r in zip(lens, res):
+            if rnd.random() <= -0.0682 * l + 1.364:
+                continue
+            L.append(l); R.append(r); total += l
+            if r == 1:
+                bw += 1
+                if rnd.random() < (ww - bw) / (bw * 1.3):
+                    L.append(l); R.append(r); total += l; bw += 1
+            elif r == -1:
+                ww += 1
+                if rnd.random() < (bw - ww) / (ww * 1.02):
+                    L.append(l); R.append(r); total += l; ww += 1
+            while total > 12000:
+                total -= L.pop(0)
+                r0 = R.pop(0)
+                bw -= r0 == 1; ww -= r0 == -1
+        means.append(np.mean(L)); blacks.append(np.mean(np.array(R) == 1))
+    ref_mean, ref_black = g["lens"].mean(), (g["results"] == 1).mean()
+    assert abs(np.mean(means) - ref_mean) < 2.2, (np.mean(means), ref_mean)
+    assert abs(np.mean(blacks) - ref_black) < 0.08, (np.mean(blacks), ref_black)
+    assert 9 <= min(lens) and max(lens) <= 121 and (np.array(res) == 0).mean() < 0.02
+    sp.engine.close(); net.close()
