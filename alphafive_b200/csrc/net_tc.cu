@@ -1440,7 +1440,7 @@ struct a5_tc_state {
   // with no measurable change of the output error (profiles/r02_lo_bits.txt).  A5_TC_LO_DROP=0..8 overrides.
   int lo_drop = 4;
   uint32_t lo_add = 0, lo_mask = 0xFFFFFFFFu;   // both fp16 lanes of a packed pair
-  int mega = 0;                 // A5_TC_MEGA=1: all block convs as one chunk-major launch (k_tc_mega)
+  int mega = 0;                 // all block convs as one chunk-major launch (k_tc_mega); default: S >= 13, A5_TC_MEGA=0/1
   int merge = 1;                // A5_TC_MERGE=0: run block3-conv1 / block4-conv1 separately
   long long plane_rows = 0;
   int fold = 1;
@@ -1511,7 +1511,9 @@ int tc_alloc(a5_net* net) {
   tc->pdl = ((ev = getenv("A5_TC_PDL")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge2 = ((ev = getenv("A5_TC_MERGE2")) && atoi(ev) == 0) ? 0 : 1;
   tc->merge = ((ev = getenv("A5_TC_MERGE")) && atoi(ev) == 0) ? 0 : 1;
-  tc->mega = ((ev = getenv("A5_TC_MEGA")) && atoi(ev) != 0) ? 1 : 0;
+  // chunk-major megakernel: measured +3 % at 15x15 (256 positions per board = whole tiles, chunks of 4 boards) and
+  // +0.7 % at 11x11 (within run-to-run noise): on by default for boards of 13x13 and more, A5_TC_MEGA=0/1 forces it
+  tc->mega = (ev = getenv("A5_TC_MEGA")) ? (atoi(ev) != 0) : (net->S >= 13);
   if ((ev = getenv("A5_TC_LO_DROP")) && atoi(ev) >= 0 && atoi(ev) <= 8) tc->lo_drop = atoi(ev);
   {
     const uint32_t d = (uint32_t)tc->lo_drop, r = d ? (1u << (d - 1)) : 0u, m = ~((1u << d) - 1u) & 0xFFFFu;

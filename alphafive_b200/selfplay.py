@@ -119,6 +119,8 @@ class SelfPlay:
             cnt = out[3 * i + 2]
             if cnt > 0:
                 table[nm] = (out[3 * i] / cnt / 1000.0, out[3 * i + 1] / cnt / 1000.0)
+        if "k_tc_conv2[0]" in table and "k_tc_conv2[1]" not in table:      # one launch for all block convs
+            table = {("k_tc_mega" if k == "k_tc_conv2[0]" else k): v for k, v in table.items()}
         return table
 
     def harvest_games(self):

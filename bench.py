@@ -275,14 +275,16 @@ def conv_roofline(kt, S, N, pk, traffic):
     block3/block4 conv2; 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass /
     in-situ time of those launches (predecessor's end -> own end inside the CUDA-graph replay)."""
     C = S * S
-    names = [f"k_tc_conv2[{i}]" for i in range(8)]
+    names = [f"k_tc_conv2[{i}]" for i in range(8)] + ["k_tc_mega"]
     conv_us = sum(kt[n][0] for n in names if n in kt)
+    mega = "k_tc_mega" in kt
     conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
     ach = conv_flop / (conv_us * 1e-6) / 1e12
     net_us = sum(v[0] for k, v in kt.items() if k not in ("k_step", "(fold)"))
     flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * C / 121) * N
     tr = traffic.get("conv_dram_bytes_per_pass") * N / 4096.0 * (C / 121.0) if traffic else None
-    return {"bound": "tensor", "kernel": "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)",
+    return {"bound": "tensor", "kernel": ("k_tc_mega (the eight block-conv layers as one chunk-major tcgen05 cta_group::2 launch)" if mega else
+                                          "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)"),
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
             "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
             "timing": "in situ: %globaltimer stamps of every launch inside CUDA-graph replays of the running workload; "
