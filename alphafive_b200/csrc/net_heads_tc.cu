@@ -12,7 +12,7 @@
 
 namespace a5 {
 
-constexpr int FC_STAGES = 4;
+constexpr int FC_STAGES = 6;                             // at most; the launch passes how many fit (227 KB)
 constexpr int FC_A_BYTES = 2 * 4 * 128 * 16;            // 16 KB per stage (K = 32)
 constexpr int FC_THREADS = 192;
 
@@ -35,8 +35,10 @@ struct FCBarriers {
   uint32_t tmem_base, pad;
 };
 
+// `nring` stages of (A 16 KB + weights) are in flight per CTA: the kernel is bound by the L2 -> shared-memory stream of
+// its 2 MB of operands, i.e. by bytes in flight over the ~2 us L2 latency -- six stages at 11x11 (192 KB), four at 15x15
 __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__ FCHead P, const __grid_constant__ FCHead V,
-                                                         int mtiles, int n) {
+                                                         int mtiles, int n, int nring) {
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_launch_dependents();
   kt_begin(P.kt);
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
   const int N = H.N;
   const uint32_t w_bytes = 4u * 2u * (uint32_t)N * 16u;
   const uint32_t stride = FC_A_BYTES + ((w_bytes + 1023u) & ~1023u);
-  FCBarriers* B = (FCBarriers*)(smem + FC_STAGES * stride);
+  FCBarriers* B = (FCBarriers*)(smem + nring * stride);
   float* s_bias = (float*)((uint8_t*)B + 128);           // [256] bias, then [64] fc2 kernel, [1] fc2 bias
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
     if (threadIdx.x == 64) s_bias[256 + 64] = H.b2[0];
   }
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < FC_STAGES; ++i) { mbar_init(&B->full[i], 1); mbar_init(&B->empty[i], 1); }
+    for (int i = 0; i < nring; ++i) { mbar_init(&B->full[i], 1); mbar_init(&B->empty[i], 1); }
     mbar_init(&B->t_full, 1);
     fence_barrier_init();
   }
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
         bulk_g2s(smem + st * stride + FC_A_BYTES, w_src + (size_t)k * (w_bytes / 2), w_bytes, &B->full[st]);
       }
       __syncwarp();
-      if (++st == FC_STAGES) { st = 0; ph ^= 1; }
+      if (++st == nring) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_tc_fc(const __grid_constant__
         if (k == H.nst - 1) tc_commit(&B->t_full);
       }
       __syncwarp();
-      if (++st == FC_STAGES) { st = 0; ph ^= 1; }
+      if (++st == nring) { st = 0; ph ^= 1; }
     }
   } else {
     // ===================== epilogue: thread = board =====================
@@ -213,7 +215,7 @@ struct HeadsState {
   __half* a_pol = nullptr; __half* a_val = nullptr;    // head-conv outputs (A operands)
   __half* w_pol = nullptr; __half* w_val = nullptr;
   float* pconv_w = nullptr; float* pconv_b = nullptr;   // 1x1 32->16 kernel [32][16] and bias
-  int nst_pol = 0, nst_val = 0, n_pol = 0, mtiles = 0, smem = 0;
+  int nst_pol = 0, nst_val = 0, n_pol = 0, mtiles = 0, smem = 0, nring = 0;
 };
 
 int heads_alloc(a5_net* net, HeadsState** out) {
@@ -234,7 +236,10 @@ int heads_alloc(a5_net* net, HeadsState** out) {
   A5_CUDA(cudaMalloc(&h->pconv_w, 32 * 16 * 4));
   A5_CUDA(cudaMalloc(&h->pconv_b, 16 * 4));
   const uint32_t wb = 4u * 2u * (uint32_t)h->n_pol * 16u;
-  h->smem = FC_STAGES * (FC_A_BYTES + (int)((wb + 1023u) & ~1023u)) + 128 + (256 + 64 + 4) * 4 + 128;
+  const int stride = FC_A_BYTES + (int)((wb + 1023u) & ~1023u), misc = 128 + (256 + 64 + 4) * 4 + 128;
+  h->nring = (232448 - misc) / stride;
+  if (h->nring > FC_STAGES) h->nring = FC_STAGES;
+  h->smem = h->nring * stride + misc;
   A5_CUDA(cudaFuncSetAttribute(k_tc_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   return A5_OK;
 }
@@ -269,7 +274,7 @@ int heads_forward(a5_net* net, HeadsState* h, int n, float* prob, float* value, 
   V.nst = h->nst_val; V.N = 64; V.C = 64; V.fold = 1;
   P.kt = kt_slot(KT_HEADS);
   const int mtiles = (n + 127) / 128;
-  A5_CUDA(launch_pdl_k(k_tc_fc, (unsigned)(2 * mtiles), FC_THREADS, (size_t)h->smem, st, pdl_enabled(), P, V, mtiles, n));
+  A5_CUDA(launch_pdl_k(k_tc_fc, (unsigned)(2 * mtiles), FC_THREADS, (size_t)h->smem, st, pdl_enabled(), P, V, mtiles, n, h->nring));
   A5_CUDA(cudaGetLastError());
   return A5_OK;
 }
