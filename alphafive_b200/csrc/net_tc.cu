@@ -1578,6 +1578,7 @@ static cudaEvent_t* g_tc_events = nullptr;
 static bool g_tc_keep_head_acts = false;           // a5__debug_activation wants block3/5 outputs stored too
 static unsigned long long* g_tc_dbg = nullptr;   // a5__debug_timeline: [10 layers][4 roles][256]
 static unsigned long long* g_tc_clk = nullptr;   // a5__debug_clk: [8 conv launches][4]
+static unsigned long long* g_tc_mega_dbg = nullptr;   // a5__debug_mega_clk: [nchunks * layers + 1][2]
 #define TC_MARK(i) do { if (g_tc_events) cudaEventRecord(g_tc_events[i], st); } while (0)
 
 // heads + biases come from the fp32 path's packed copies (fp32_set_weights runs first)
@@ -1700,7 +1701,7 @@ int tc_forward(a5_net* net, const int8_t* planes, int n, float* prob, float* val
     M.CB = cb;
     M.gpc = (cb * ps.per_board + 255) / 256;
     M.nchunks = (bmax + cb - 1) / cb;
-    M.dbg = g_tc_clk;                                  // a5__debug_clk: in mega mode [(nchunks * nl + 1)][2]
+    M.dbg = g_tc_mega_dbg;                             // a5__debug_mega_clk: [(nchunks * nl + 1)][2]
     M.kt = kt_slot(KT_CONV0);
     const bool h16 = ps.pitch + 1 <= 16;
     const int slab = h16 ? TCfgH<2, 16>::SLAB : TCfgH<2, 24>::SLAB;
@@ -1776,6 +1777,9 @@ int a5__debug_ktime_read(double* h_out) {
 // internal tooling: device buffer uint64 [8][4] receiving {clock64, globaltimer} at start / end of CTA 0 of every
 // block-conv launch from now on (null: off) -- the SM clock each layer actually ran at
 int a5__debug_clk(unsigned long long* d_buf) { g_tc_clk = d_buf; return A5_OK; }
+// the same for the chunk-major megakernel: uint64 [nchunks * 8 + 1][2] = {%globaltimer, clock64} when CTA 0's issuer starts
+// each (chunk, layer), and at the kernel's end
+int a5__debug_mega_clk(unsigned long long* d_buf) { g_tc_mega_dbg = d_buf; return A5_OK; }
 
 // internal tooling: also store the block3 / block5 activations (normally consumed in-register by
 // the fused head convs) so a5__debug_activation can show them.

@@ -9,13 +9,13 @@ from alphafive_b200.net import DeviceNet, glorot_init
 S, n = 11, int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = 400
 lib = _lib.load()
-lib.a5__debug_clk.argtypes = [C.c_void_p]
+lib.a5__debug_mega_clk.argtypes = [C.c_void_p]
 net = DeviceNet(S, n, glorot_init(S, 0))
 planes = torch.from_numpy((np.random.default_rng(0).random((n, 3, S, S)) < 0.2).astype(np.int8)).cuda()
 prob = torch.empty((n, S * S), device="cuda"); val = torch.empty((n,), device="cuda")
 nl, nch = 8, 4
 clk = torch.zeros((nch * nl + 1, 2), dtype=torch.int64, device="cuda")
-check(lib.a5__debug_clk(ptr(clk)))
+check(lib.a5__debug_mega_clk(ptr(clk)))
 acc = np.zeros((nl, 2)); tot = np.zeros(2); k = 0
 for r in range(reps):
     net.forward(planes, prob, val)
