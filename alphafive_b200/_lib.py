@@ -82,6 +82,16 @@ _SIGS = {
     "a5_net_destroy": (_I, [_P]),
     "a5_net_set_weights": (_I, [_P, C.POINTER(_P), _P]),
     "a5_net_forward": (_I, [_P, _P, _I, _P, _P, _I, _P]),
+    "a5_engine_step_served": (_I, [_P, _P, _P, _P, _P]),
+    "a5_evalcache_create": (_I, [_I, _I, _I, _I, C.POINTER(_P)]),
+    "a5_evalcache_destroy": (_I, [_P]),
+    "a5_evalcache_clear": (_I, [_P, _P]),
+    "a5_evalcache_lookup": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "a5_evalcache_planes": (_P, [_P]),
+    "a5_evalcache_prob": (_P, [_P]),
+    "a5_evalcache_value": (_P, [_P]),
+    "a5_evalcache_commit": (_I, [_P, _P, _P, _P]),
+    "a5_evalcache_stats": (_I, [_P, C.POINTER(C.c_int64), _P]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -47,6 +47,7 @@ struct EP {
   uint8_t* out_rec; int32_t* out_count;
   long long* gstat;
   int8_t* planes;
+  const uint8_t* served;        // a5_engine_step_served: 0 = this game's pending leaf was not evaluated this pass (or null)
   unsigned long long* kt;       // tooling: in-situ kernel timing slot (common.cuh), or null
 };
 
@@ -659,6 +660,12 @@ __device__ __forceinline__ void step_body(const EP& P, const float* __restrict__
     if (lane == 0) P.need_eval[g] = 0;
     return;
   }
+  if (P.need_eval[g] && prob && P.served && !P.served[g]) {
+    // the evaluation cache's compact batch was full (a5_evalcache_lookup): the leaf stays pending, nothing else
+    // happens to this game in this pass
+    if (g == 0 && lane == 0) P.gstat[9] += 1;              // (passes are counted through game 0)
+    return;
+  }
   const unsigned long long dbg_t0 = g_step_dbg_on ? step_now() : 0ull;
   unsigned dbg_flags = 0;
   Warp<NCH> W(P, g, lane, s_board[wid], s_f[wid]);
@@ -1134,6 +1141,14 @@ int a5_engine_set_roots(a5_engine* e, const int8_t* d_boards, const int32_t* d_l
   if (e->p.auto_play) { set_error("a5_engine_set_roots: engine is in auto_play mode"); return A5_ERR_STATE; }
   DISPATCH(k_set_roots, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_boards, d_last, d_active, d_clear);
   return A5_OK;
+}
+
+int a5_engine_step_served(a5_engine* e, const float* d_prob, const float* d_value, const uint8_t* d_served, void* stream) {
+  A5_ARG(e && d_prob && d_value && d_served);
+  e->p.served = d_served;
+  int rc = a5_engine_step(e, d_prob, d_value, stream);
+  e->p.served = nullptr;
+  return rc;
 }
 
 int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void* stream) {

@@ -98,6 +98,19 @@ class SearchEngine:
             self._first = False
         check(self.lib.a5_engine_step(self.handle, ptr(prob), ptr(value), stream_ptr()))
 
+    def step_served(self, prob, value, served):
+        """step() when an evaluation cache decided which pending leaves were evaluated this pass (served uint8 [N])."""
+        check(self.lib.a5_engine_step_served(self.handle, ptr(prob), ptr(value), ptr(served), stream_ptr()))
+
+    def cached_pass(self, net, cache, prob, value, net_mode=None):
+        """One search pass through a cross-game evaluation cache (selfplay.EvalCache): table hits are copied to
+        the games' rows, the misses go through the network as a compact batch, the rest waits a pass."""
+        check(self.lib.a5_evalcache_lookup(cache.handle, self.planes_ptr, self.lib.a5_engine_need_eval(self.handle), ptr(prob),
+                                           ptr(value), ptr(cache.served), stream_ptr()))
+        net.forward_raw(cache.planes_ptr, cache.cap, cache.cprob, cache.cvalue, net_mode)
+        check(self.lib.a5_evalcache_commit(cache.handle, ptr(prob), ptr(value), stream_ptr()))
+        self.step_served(prob, value, cache.served)
+
     def planes(self) -> torch.Tensor:
         """Zero-copy int8 [N,3,S,S] view of the leaf planes written by the last pass."""
         return _view(self.planes_ptr, (self.N, 3, self.S, self.S), torch.int8, self.device)
@@ -171,12 +184,13 @@ class SearchEngine:
         return buf[:cnt.value], games.value
 
     # -- convenience: run until every game's budget is spent (auto_play = 0) ------
-    def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None, active=None):
+    def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None, active=None, cache=None):
         """Drive step/forward until no game is busy.  ``net`` is a DeviceNet (on-device
         leaf evaluation, ``net_mode`` overrides its compute path); ``pv_fn`` is a reference-style host callable.
         ``active`` (bool / uint8 [N] device tensor, the mask given to set_roots): when fewer than ~3/4 of the slots
         search -- the arena, where each player only moves in half of the games (choose_best_player.py:48-52) -- only
-        their leaves go through the network (gather planes -> forward -> scatter prob / value)."""
+        their leaves go through the network (gather planes -> forward -> scatter prob / value).  ``cache``: a
+        selfplay.EvalCache shared by the games of this engine (on-device net only)."""
         assert (net is None) != (pv_fn is None)
         if self._prob is None:
             self._prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
@@ -223,25 +237,33 @@ class SearchEngine:
                     if self.busy() == 0:
                         break
                     continue
-                key = (id(net), net_mode, self._version)
+                if cache is not None and cache.net_version != net.version:
+                    cache.clear()                             # cached results belong to one set of weights
+                    cache.net_version = net.version
+
+                def one_pass():
+                    if cache is not None:
+                        self.cached_pass(net, cache, prob, value, net_mode)
+                    else:
+                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
+                        self.step(prob, value)
+
+                key = (id(net), net_mode, self._version, id(cache))
                 if self.use_graph and left >= 4 and self._graph_key != key:
                     # one eager pass (counts), then capture the pass; replays keep the launch gaps off the GPU
-                    net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
-                    self.step(prob, value)
+                    one_pass()
                     left -= 1
                     torch.cuda.current_stream().synchronize()
                     self._graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self._graph):
-                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
-                        self.step(prob, value)
+                        one_pass()
                     self._graph_key = key
                 if self.use_graph and self._graph_key == key:
                     for _ in range(left):
                         self._graph.replay()
                 else:
                     for _ in range(left):
-                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
-                        self.step(prob, value)
+                        one_pass()
                 if self.busy() == 0:
                     break
                 continue

@@ -65,6 +65,7 @@ class DeviceNet:
             check(self.lib.a5_net_create(S, max_batch, C.byref(h)))
         self.handle = h
         self.names = tensor_names()
+        self.version = 0                        # bumped by set_weights (evaluation caches key on it)
         self.params: dict[str, torch.Tensor] = {}
         self.set_weights(weights if weights is not None else glorot_init(S))
 
@@ -80,6 +81,7 @@ class DeviceNet:
         with torch.cuda.device(self.device):
             check(self.lib.a5_net_set_weights(self.handle, arr, stream_ptr()))
         self.params = params          # PyTorch keeps ownership of the fp32 masters
+        self.version += 1
 
     def forward(self, planes: torch.Tensor, prob: torch.Tensor | None = None, value: torch.Tensor | None = None,
                 mode: int | None = None):

@@ -21,9 +21,62 @@ from .replay import gather_records, parse_records, records_to_games
 from .net import DeviceNet
 
 
+class EvalCache:
+    """Cross-game evaluation cache (a5_evalcache_*): leaves whose position some game of the batch has had evaluated
+    before are served from a device table; the others go through the network as a compact batch of ``cap`` boards.
+    ``cap`` defaults to the largest batch that needs one group per CTA less than ``n_games`` boards would."""
+
+    def __init__(self, S, n_games, log2_slots=21, cap=None, num_sms=None):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check
+        self.lib = _lib.load()
+        if cap is None:
+            sms = num_sms or torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            per_board, ctas = (S + 1) * (S + 1), sms & ~1
+            groups = -(-(n_games * per_board) // 256)                  # groups of 256 positions in the full batch
+            per_cta = -(-groups // ctas)
+            cap = min(n_games, ((per_cta - 1) * ctas * 256) // per_board) if per_cta > 1 else n_games
+            if cap < 0.9 * n_games:                                   # not worth deferring a tenth of the leaves
+                cap = n_games
+        self.S, self.N, self.cap = S, n_games, int(cap)
+        h = C.c_void_p()
+        check(self.lib.a5_evalcache_create(S, n_games, log2_slots, self.cap, C.byref(h)))
+        self.handle = h
+        self.planes_ptr = self.lib.a5_evalcache_planes(h)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        from .engine import _view
+        self.cprob = _view(self.lib.a5_evalcache_prob(h), (self.cap, S * S), torch.float32, dev)
+        self.cvalue = _view(self.lib.a5_evalcache_value(h), (self.cap,), torch.float32, dev)
+        self.served = torch.ones((n_games,), dtype=torch.uint8, device=dev)
+        self.net_version = None
+
+    def clear(self):
+        from ._lib import check, stream_ptr
+        check(self.lib.a5_evalcache_clear(self.handle, stream_ptr()))
+
+    def stats(self) -> dict:
+        import ctypes as C
+        from ._lib import check, stream_ptr
+        arr = (C.c_int64 * 4)()
+        check(self.lib.a5_evalcache_stats(self.handle, arr, stream_ptr()))
+        return dict(lookups=arr[0], hits=arr[1], deferred=arr[2], stored=arr[3])
+
+    def close(self):
+        if self.handle:
+            self.lib.a5_evalcache_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SelfPlay:
     def __init__(self, cfg=None, n_games=4096, net: DeviceNet | None = None, training=True, seed=0,
-                 game_id_base=0, use_graph=True, _defer_net=False, **cfg_kw):
+                 game_id_base=0, use_graph=True, _defer_net=False, eval_cache=False, **cfg_kw):
         self.config = make_config(cfg, n_games=n_games, training=training, auto_play=True, seed=seed,
                                   game_id_base=game_id_base, **cfg_kw)
         self.engine = SearchEngine(self.config)
@@ -38,13 +91,27 @@ class SelfPlay:
         self._graph = None
         self._started = False
         self.passes = 0
+        # eval_cache: True, or dict(log2_slots=..., cap=...) -- see EvalCache
+        self.cache = None
+        if eval_cache:
+            self.cache = EvalCache(self.S, n_games, **(eval_cache if isinstance(eval_cache, dict) else {}))
 
     # one pass = network forward over all N pending leaves + one tree-kernel pass
     def _pass(self):
-        self.net.forward_raw(self.engine.planes_ptr, self.N, self.prob, self.value)
-        self.engine.step(self.prob, self.value)
+        if self.cache is None:
+            self.net.forward_raw(self.engine.planes_ptr, self.N, self.prob, self.value)
+            self.engine.step(self.prob, self.value)
+            return
+        self.engine.cached_pass(self.net, self.cache, self.prob, self.value)
+
+    def _check_cache(self):
+        """Cached results belong to one set of weights."""
+        if self.cache is not None and self.cache.net_version != self.net.version:
+            self.cache.clear()
+            self.cache.net_version = self.net.version
 
     def start(self):
+        self._check_cache()
         if not self._started:
             self.engine.step()              # first descent: every game reaches its (unseen) root
             self._started = True
@@ -72,6 +139,7 @@ class SelfPlay:
                 self._pass()
 
     def run_passes(self, k: int):
+        self._check_cache()
         self.start()
         if self._graph is not None:
             for _ in range(k):
@@ -217,7 +285,7 @@ class BatchedPlayer:
     """N reference ``Player`` objects in lock-step, host buffers in and out."""
 
     def __init__(self, cfg=None, n_players=1, net: DeviceNet | None = None, training=True, random_a=False,
-                 seed=0, game_id_base=0, check_every=16, **cfg_kw):
+                 seed=0, game_id_base=0, check_every=16, eval_cache=False, **cfg_kw):
         self.config = make_config(cfg, n_games=n_players, training=training, random_a=random_a,
                                   auto_play=False, seed=seed, game_id_base=game_id_base, **cfg_kw)
         self.engine = SearchEngine(self.config)
@@ -225,6 +293,9 @@ class BatchedPlayer:
         self.C = self.S * self.S
         self.net = net if net is not None else DeviceNet(self.S, n_players)
         self.check_every = check_every
+        # eval_cache: True, dict(log2_slots=..., cap=...) or an EvalCache to share (see EvalCache)
+        self.cache = eval_cache if isinstance(eval_cache, EvalCache) else (
+            EvalCache(self.S, n_players, **(eval_cache if isinstance(eval_cache, dict) else {})) if eval_cache else None)
         dev = self.engine.device
         N, S, C = self.N, self.S, self.C
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
@@ -245,7 +316,7 @@ class BatchedPlayer:
         self.d_boards.copy_(self.h_boards, non_blocking=True)
         self.d_last.copy_(self.h_last, non_blocking=True)
         self.engine.set_roots(self.d_boards, self.d_last, active, clear)
-        self.engine.run_search(net=self.net, check_every=self.check_every)
+        self.engine.run_search(net=self.net, check_every=self.check_every, cache=self.cache)
         policy, action = self.engine.finish_move()
         self.h_policy.copy_(policy, non_blocking=True)
         self.h_action.copy_(action, non_blocking=True)

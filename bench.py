@@ -55,6 +55,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg4 / cfg5 / cfg1 legs")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eval-cache", type=int, default=int(os.environ.get("A5_EVAL_CACHE", "1")),
+                    help="1: cross-game evaluation cache + compact leaf batch in the lock-step self-play runs (a5_evalcache_*); "
+                         "2: also in the end-to-end BatchedPlayer leg (there every search of a call starts together, demand "
+                         "exceeds the compact batch in some calls and the stragglers cost what the smaller forward gains: "
+                         "measured equal on average, profiles/r02_evalcache.txt); 0: off")
     return ap.parse_args()
 
 
@@ -271,7 +276,7 @@ def workload_name(a, world):
 
 # --------------------------------------------------------------------------------------
 def conv_roofline(kt, S, N, pk, traffic):
-    """Dominant kernel = k_tc_conv2 (eight launches per pass: block3/block4 conv1 run as one layer, and so do
+    """N = boards per network forward (the compact batch when the evaluation cache is on).  Dominant kernel = k_tc_conv2 (eight launches per pass: block3/block4 conv1 run as one layer, and so do
     block3/block4 conv2; 98.9 % of the algorithmic FLOPs).  achieved = algorithmic conv FLOPs of one pass /
     in-situ time of those launches (predecessor's end -> own end inside the CUDA-graph replay)."""
     C = S * S
@@ -348,6 +353,7 @@ def run_ours(a):
     weights = glorot_init(S, 0)
     net = DeviceNet(S, N, weights, mode=mode)
     sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
+                  eval_cache=bool(a.eval_cache) and mode == _lib.NET_TC,
                   board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
     stride = sp.engine.record_stride
     stack = RandomStack(S, length=a.buffer)                  # the sink: every rank keeps the whole replay buffer
@@ -447,14 +453,25 @@ def run_ours(a):
     e2e_steps = a.e2e_steps if a.e2e_steps is not None else max(a.steps, 8)
     d_boards, d_last = sp.engine.roots()
     boards, last = d_boards.cpu().numpy(), d_last.cpu().numpy()
-    launches_per_pass = 12 if mode == _lib.NET_TC else 16
     occupancy = stack.count / stack.length
+    cache_info = None
+    if sp.cache is not None:
+        st = sp.cache.stats()
+        cache_info = {"boards_per_forward": sp.cache.cap, "of_games": N, "lookups": st["lookups"],
+                      "hit_rate": st["hits"] / max(1, st["lookups"]), "deferred_rate": st["deferred"] / max(1, st["lookups"]),
+                      "stored": st["stored"], "_hits": st["hits"], "_deferred": st["deferred"],
+                      "note": "since the start of the run (preroll and warm-up included); leaves served from earlier network "
+                              "results of any game, the rest evaluated as a compact batch (a5_evalcache_*); per-game results "
+                              "are bit-identical to the uncached run (tests/test_gpu_mcts.py)"}
+    shared_cache = sp.cache                                  # warm: the end-to-end leg below searches with the same weights
+    launches_per_pass = (12 if mode == _lib.NET_TC else 16) + (3 if cache_info is not None else 0)
     sp.engine.close()
     del sp, stack, bufs
     torch.cuda.empty_cache()
-    e2e_val, e2e_calls, bp_bytes = None, [], (0, 0)
+    e2e_val, e2e_calls, bp_bytes, e2e_cache = None, [], (0, 0), None
     if e2e_steps > 0:
         bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
+                           eval_cache=shared_cache if (shared_cache is not None and a.eval_cache >= 2) else False,
                            board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
         bp_bytes = (bp.h2d_bytes, bp.d2h_bytes)
         clear = np.ones(N, np.uint8)
@@ -474,15 +491,25 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_val = N * world * len(e2e_calls) / e2e_t.item()
+        if bp.cache is not None:
+            st = bp.cache.stats()
+            e2e_cache = {"lookups": st["lookups"] - cache_info["lookups"], "hit_rate": (st["hits"] - cache_info["_hits"]) / max(1, st["lookups"] - cache_info["lookups"]),
+                         "deferred_rate": (st["deferred"] - cache_info["_deferred"]) / max(1, st["lookups"] - cache_info["lookups"])}
         bp.engine.close()
         del bp
         torch.cuda.empty_cache()
+    if shared_cache is not None:
+        shared_cache.close()
 
     out = None
     if rank == 0:
         pk = peaks()
         out = {
             "metric": METRIC, "value": value, "unit": "moves/s", "leaf_evals_per_s": evals / (ms / 1000),
+            "leaf_evals_note": ("leaves expanded with a network result per second; with the evaluation cache a pass sends "
+                                "`eval_cache.boards_per_forward` boards through the network and serves the other leaves from "
+                                "earlier results" if cache_info else "leaves expanded = boards through the network"),
+            "nn_boards_per_s": (cache_info["boards_per_forward"] if cache_info else N) * world * passes_timed / (ms / 1000),
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if mode == _lib.NET_FP32 else "f16x2-split (fp32 accumulate)", "data": "synthetic",
@@ -510,12 +537,18 @@ def run_ours(a):
                        "sink": "RandomStack.push_records on every rank (utils.py:64-116 decisions, device ring)"},
             "clocks": clocks,
         }
+        if cache_info is not None:
+            out["eval_cache"] = {k: v for k, v in cache_info.items() if not k.startswith("_")}
+            if e2e_cache is not None:
+                out["eval_cache"]["e2e_leg"] = e2e_cache
         if kt is not None:
             out["kernels_us_per_pass"] = {k: [round(v[0], 2), round(v[1], 2)] for k, v in kt.items()}
             out["kernels_note"] = ("[predecessor end -> own end, own first start -> own end] per kernel, mean over "
                                    f"{a.accounting_passes} CUDA-graph replays right after the timed region; the first values sum to "
                                    "the accounted pass")
-            out["roofline"] = conv_roofline(kt, S, N, pk, measured_traffic())
+            n_fwd = cache_info["boards_per_forward"] if cache_info else N
+            out["roofline"] = conv_roofline(kt, S, n_fwd, pk, measured_traffic())
+            out["roofline"]["boards_per_forward"] = n_fwd
             out["roofline_tree"] = tree_roofline(kt, c1, c2, S, pk)
             # the stamps cost ~1 % (atomics, one extra CTA barrier per kernel) and the fold kernel is instrumentation only
             out["ms_per_pass_accounted"] = sum(v[0] for k, v in kt.items() if k != "(fold)") / 1000.0
@@ -575,6 +608,7 @@ def run_configs(a, rank, world, net11, mode):
         S, N, sims, upper = 15, a.games, 800, 900
         net = DeviceNet(S, N, glorot_init(S, 0), mode=mode)
         sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, board_size=S,
+                      eval_cache=bool(a.eval_cache) and mode == _lib.NET_TC,
                       simulation_per_step=sims, upper_simulation_per_step=upper)
         sp.start()
         sp.set_budget(40, 50)
@@ -605,7 +639,9 @@ def run_configs(a, rank, world, net11, mode):
                        "leaf_evals_per_s": ev / (mx / 1000), "steps": steps4, "ms_per_step": mx / steps4,
                        "overflows": c1["overflows"], "max_nodes": c1["max_nodes"], "flop_per_leaf": FLOP_PER_LEAF[15]}
         if kt:
-            out["cfg4"]["roofline"] = conv_roofline(kt, S, N, pk, None)
+            n_fwd = sp.cache.cap if sp.cache is not None else N
+            out["cfg4"]["roofline"] = conv_roofline(kt, S, n_fwd, pk, None)
+            out["cfg4"]["roofline"]["boards_per_forward"] = n_fwd
             out["cfg4"]["roofline_tree"] = tree_roofline(kt, c1, c2, S, pk)
             out["cfg4"]["kernels_us_per_pass"] = {k: [round(v[0], 2), round(v[1], 2)] for k, v in kt.items()}
         sp.engine.close()

@@ -121,6 +121,9 @@ int a5_engine_set_roots(a5_engine* e, const int8_t* d_boards, const int32_t* d_l
  * written to a5_engine_planes()[i] with a5_engine_need_eval()[i] = 1.  Pass NULL
  * prob/value on the very first pass after create/reset/set_roots. */
 int a5_engine_step(a5_engine* e, const float* d_prob, const float* d_value, void* stream);
+/* The same when not every pending leaf was evaluated this pass (a5_evalcache_lookup): games with
+ * d_served[i] == 0 keep their pending leaf and do nothing in this pass. */
+int a5_engine_step_served(a5_engine* e, const float* d_prob, const float* d_value, const uint8_t* d_served, void* stream);
 
 /* Per-call arguments of the reference API that are engine state here: the `training`
  * attribute / `random_a` argument of get_action (player.py:24,128) and the lazily read
@@ -239,6 +242,30 @@ int a5_net_set_weights(a5_net* net, const float* const* d_tensors, void* stream)
 /* prob f32[n][S*S] (softmax over all cells), value f32[n] = tanh(x/2). */
 int a5_net_forward(a5_net* net, const int8_t* d_planes, int n, float* d_prob, float* d_value,
                    int mode, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Cross-game evaluation cache for lock-step self-play.  evaluate_and_expand asks pv_fn for every
+ * unseen position (player.py:186-202); thousands of games in one batch ask for many positions more
+ * than once (openings).  The network is a deterministic, batch-invariant function of its input
+ * planes, so serving a leaf from a table of earlier results is exact.  Per pass:
+ *   a5_evalcache_lookup  hits -> d_prob / d_value rows of the game; misses -> a compact batch of at
+ *                        most `cap` boards (a5_evalcache_planes); leaves that do not fit stay pending
+ *                        (d_served[i] = 0, see a5_engine_step_served)
+ *   a5_net_forward       on a5_evalcache_planes() with n = cap -> a5_evalcache_prob() / _value()
+ *   a5_evalcache_commit  compact results -> the games' rows and into the table
+ * a5_evalcache_clear must follow every a5_net_set_weights. */
+typedef struct a5_evalcache a5_evalcache;
+int a5_evalcache_create(int S, int n_games, int log2_slots, int cap, a5_evalcache** out);
+int a5_evalcache_destroy(a5_evalcache* c);
+int a5_evalcache_clear(a5_evalcache* c, void* stream);
+int a5_evalcache_lookup(a5_evalcache* c, const int8_t* d_planes, const uint8_t* d_need, float* d_prob, float* d_value,
+                        uint8_t* d_served, void* stream);
+int8_t* a5_evalcache_planes(a5_evalcache* c);
+float* a5_evalcache_prob(a5_evalcache* c);
+float* a5_evalcache_value(a5_evalcache* c);
+int a5_evalcache_commit(a5_evalcache* c, float* d_prob, float* d_value, void* stream);
+/* h_out[4]: lookups, hits, leaves deferred (batch full), entries stored -- since create. */
+int a5_evalcache_stats(a5_evalcache* c, int64_t* h_out, void* stream);
 
 /* The tensor-core forward in three stream-ordered parts, for callers that pipeline two half batches on
  * SM-partitioned streams (CUDA green contexts): FRONT = input bitboards + conv1, BODY = the nine block

@@ -239,3 +239,64 @@ def test_record_arena_overflow_is_loud_and_never_splits_a_game(cuda_lib):
     assert games >= 3 and i > 400 - 121
     assert eng.counters()["records_dropped"] > 0
     eng.close()
+
+
+@pytest.mark.parametrize("cap", [None, 40])
+def test_evaluation_cache_plays_the_same_games(cuda_lib, cap):
+    """Cross-game evaluation cache (a5_evalcache_*): leaves served from the table of earlier network results, the
+    rest evaluated as a compact batch; with cap < N some leaves wait a pass.  The network is deterministic and
+    batch-invariant and every game has its own counter-based RNG stream, so every game must come out bit for bit
+    as without the cache -- positions, policies, results -- whatever pass its leaves were evaluated in."""
+    from alphafive_b200.engine import parse_records
+    from alphafive_b200.net import DeviceNet
+    from alphafive_b200.selfplay import SelfPlay
+    S, N, sims = 11, 64, 24
+
+    def play(eval_cache, want=70):
+        net = DeviceNet(S, N)
+        sp = SelfPlay(None, n_games=N, net=net, training=True, seed=4, use_graph=False, eval_cache=eval_cache,
+                      board_size=S, simulation_per_step=sims, upper_simulation_per_step=sims + 10)
+        games = {}
+        while len(games) < want:
+            sp.run_passes(400)
+            for r in parse_records(sp.harvest()[0], S):
+                games.setdefault((r["game_id"], r["game_serial"]), []).append(r)
+        stats = sp.cache.stats() if sp.cache is not None else None
+        assert sp.engine.counters()["overflows"] == 0
+        sp.engine.close(); net.close()
+        return games, stats
+
+    plain, _ = play(False)
+    cached, stats = play(dict(log2_slots=16, cap=cap) if cap else dict(log2_slots=16), want=100)     # (deferrals shift which games finish first)
+    assert stats["hits"] > 0 and stats["stored"] > 0 and (cap is None or stats["deferred"] > 0)
+    common = sorted(set(plain) & set(cached))
+    assert len(common) >= 50
+    for key in common:
+        a, b = sorted(plain[key], key=lambda r: r["ply"]), sorted(cached[key], key=lambda r: r["ply"])
+        assert len(a) == len(b) == a[0]["game_len"]
+        for ra, rb in zip(a, b):
+            assert (ra["board"] == rb["board"]).all() and ra["last_action"] == rb["last_action"]
+            assert np.array_equal(ra["policy"], rb["policy"]) and ra["value"] == rb["value"] and ra["result"] == rb["result"]
+
+
+def test_batched_player_with_evaluation_cache_returns_the_same_moves(cuda_lib):
+    """BatchedPlayer.get_actions through the evaluation cache (compact batch smaller than the number of players, so
+    some leaves wait): policies and actions equal the uncached call's bit for bit, move after move."""
+    from alphafive_b200.net import DeviceNet
+    from alphafive_b200.selfplay import BatchedPlayer
+    S, N, sims = 11, 48, 40
+    net = DeviceNet(S, N)
+    kw = dict(n_players=N, net=net, training=True, seed=9, board_size=S, simulation_per_step=sims, upper_simulation_per_step=sims + 20)
+    a = BatchedPlayer(None, **kw)
+    b = BatchedPlayer(None, eval_cache=dict(log2_slots=14, cap=36), **kw)
+    boards = np.zeros((N, S, S), np.int8)
+    last = np.full(N, -1, np.int32)
+    clear = np.ones(N, np.uint8)
+    for ply in range(6):
+        pa, aa, na, ca = a.get_actions(boards, last, clear=clear, advance=True)
+        pb, ab, nb, cb = b.get_actions(boards, last, clear=clear, advance=True)
+        assert np.array_equal(aa, ab) and np.array_equal(pa, pb) and np.array_equal(na, nb) and np.array_equal(ca, cb)
+        boards, last, clear = na.copy(), aa.copy(), np.zeros(N, np.uint8)
+    st = b.cache.stats()
+    assert st["hits"] > 0 and st["deferred"] > 0
+    a.engine.close(); b.engine.close(); net.close()
