@@ -353,7 +353,7 @@ def run_ours(a):
     weights = glorot_init(S, 0)
     net = DeviceNet(S, N, weights, mode=mode)
     sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, game_id_base=rank * N, use_graph=not a.no_graph,
-                  eval_cache=bool(a.eval_cache) and mode == _lib.NET_TC,
+                  eval_cache=(dict(cap=int(os.environ["A5_EC_CAP"])) if os.environ.get("A5_EC_CAP") else True) if (a.eval_cache and mode == _lib.NET_TC) else False,
                   board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
     stride = sp.engine.record_stride
     stack = RandomStack(S, length=a.buffer)                  # the sink: every rank keeps the whole replay buffer
