@@ -68,7 +68,8 @@ static inline cudaError_t launch_pdl_k(void (*kernel)(KArgs...), unsigned grid, 
 // ---------------------------------------------------------------------------
 constexpr int KT_SLOTS = 16;
 constexpr int KT_SUB = 32;
-enum { KT_C1BITS = 0, KT_CONV1 = 1, KT_CONV0 = 2 /* .. +7: the 8 block-conv launches */, KT_HEADS = 10, KT_STEP = 11, KT_FOLD = 12 };
+enum { KT_C1BITS = 0, KT_CONV1 = 1, KT_CONV0 = 2 /* .. +7: the 8 block-conv launches */, KT_HEADS = 10, KT_STEP = 11, KT_FOLD = 12,
+       KT_EC_LOOKUP = 13, KT_EC_COMMIT = 14 /* evaluation cache: before the bitboards / between heads and tree pass */ };
 unsigned long long* kt_slot(int slot);          // device pointer of a slot, or nullptr while timing is off (net_tc.cu)
 
 __device__ __forceinline__ unsigned long long kt_now() {

@@ -41,11 +41,26 @@ __device__ __forceinline__ uint32_t ec_mix(uint32_t h) {
   return h;
 }
 
+__device__ __forceinline__ void ec_lookup_body(const ECParams& P, const int8_t* __restrict__ planes, const uint8_t* __restrict__ need,
+                                               float* __restrict__ prob, float* __restrict__ value, uint8_t* __restrict__ served,
+                                               const int w, const int lane);
+__device__ __forceinline__ void ec_commit_body(const ECParams& P, float* __restrict__ prob, float* __restrict__ value, const int row,
+                                               const int lane);
+
 __global__ void __launch_bounds__(128) k_ec_lookup(const ECParams P, const int8_t* __restrict__ planes, const uint8_t* __restrict__ need,
-                                                   float* __restrict__ prob, float* __restrict__ value, uint8_t* __restrict__ served) {
+                                                   float* __restrict__ prob, float* __restrict__ value, uint8_t* __restrict__ served,
+                                                   unsigned long long* kt) {
   const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();                                              // the tree pass that wrote planes / need is complete
+  kt_begin(kt);
+  ec_lookup_body(P, planes, need, prob, value, served, w, lane);
+  if (kt) { __syncthreads(); kt_end(kt); }
+}
+
+__device__ __forceinline__ void ec_lookup_body(const ECParams& P, const int8_t* __restrict__ planes, const uint8_t* __restrict__ need,
+                                               float* __restrict__ prob, float* __restrict__ value, uint8_t* __restrict__ served,
+                                               const int w, const int lane) {
   if (w >= P.N) return;
   // rows of the compact batch go to whoever asks first, and late warps ask last: rotate which games those are from
   // pass to pass, or the same games would be the ones that wait whenever the batch is full
@@ -66,12 +81,15 @@ __global__ void __launch_bounds__(128) k_ec_lookup(const ECParams P, const int8_
   for (int o = 16; o; o >>= 1) h ^= __shfl_xor_sync(FULL, h, o);
   h = ec_mix(h);
   int hit = -1, empty = -1;
+  uint32_t kk[EC_PROBE];
+#pragma unroll
+  for (int j = 0; j < EC_PROBE; ++j)                        // the four probes are independent loads: all in flight at once
+    kk[j] = lane < EC_KEYW ? P.keys[(size_t)((h + (uint32_t)j) & P.mask) * EC_KEYW + lane] : 0u;
 #pragma unroll
   for (int j = 0; j < EC_PROBE; ++j) {
     const uint32_t s = (h + (uint32_t)j) & P.mask;
-    const uint32_t k = lane < EC_KEYW ? P.keys[(size_t)s * EC_KEYW + lane] : 0u;
-    const bool same = __all_sync(FULL, lane >= EC_KEYW || k == mine);
-    const bool vacant = __all_sync(FULL, lane >= EC_KEYW || k == 0u);    // an all-zero key is never stored (plane 0 or 1 has stones, or see below)
+    const bool same = __all_sync(FULL, lane >= EC_KEYW || kk[j] == mine);
+    const bool vacant = __all_sync(FULL, lane >= EC_KEYW || kk[j] == 0u);   // an all-zero key is never stored (see zero_key)
     if (same && hit < 0) hit = (int)s;
     if (vacant && empty < 0) empty = (int)s;
   }
@@ -103,10 +121,18 @@ __global__ void __launch_bounds__(128) k_ec_lookup(const ECParams P, const int8_
   }
 }
 
-__global__ void __launch_bounds__(128) k_ec_commit(const ECParams P, float* __restrict__ prob, float* __restrict__ value) {
+__global__ void __launch_bounds__(128) k_ec_commit(const ECParams P, float* __restrict__ prob, float* __restrict__ value,
+                                                   unsigned long long* kt) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();                                              // the heads kernel that wrote the compact prob / value is complete
+  kt_begin(kt);
+  ec_commit_body(P, prob, value, row, lane);
+  if (kt) { __syncthreads(); kt_end(kt); }
+}
+
+__device__ __forceinline__ void ec_commit_body(const ECParams& P, float* __restrict__ prob, float* __restrict__ value, const int row,
+                                               const int lane) {
   const int n = min(P.count[0], P.cap);
   if (row >= n) return;
   const int g = P.cgame[row];
@@ -193,7 +219,7 @@ int a5_evalcache_lookup(a5_evalcache* c, const int8_t* d_planes, const uint8_t* 
   cudaStream_t st = (cudaStream_t)stream;
   A5_CUDA(launch_pdl_k(k_ec_reset_count, 1u, 1u, 0, st, pdl_enabled(), c->p.count, c->p.N));
   A5_CUDA(launch_pdl_k(k_ec_lookup, (unsigned)((c->p.N + 3) / 4), 128u, 0, st, pdl_enabled(), c->p, d_planes, d_need, d_prob, d_value,
-                       d_served));
+                       d_served, kt_slot(KT_EC_LOOKUP)));
   return A5_OK;
 }
 
@@ -203,7 +229,7 @@ float* a5_evalcache_value(a5_evalcache* c) { return c ? c->p.cvalue : nullptr; }
 
 int a5_evalcache_commit(a5_evalcache* c, float* d_prob, float* d_value, void* stream) {
   A5_ARG(c && d_prob && d_value);
-  A5_CUDA(launch_pdl_k(k_ec_commit, (unsigned)((c->p.cap + 3) / 4), 128u, 0, (cudaStream_t)stream, pdl_enabled(), c->p, d_prob, d_value));
+  A5_CUDA(launch_pdl_k(k_ec_commit, (unsigned)((c->p.cap + 3) / 4), 128u, 0, (cudaStream_t)stream, pdl_enabled(), c->p, d_prob, d_value, kt_slot(KT_EC_COMMIT)));
   return A5_OK;
 }
 

@@ -1379,7 +1379,11 @@ __global__ void k_kt_fold(unsigned long long* kt) {
   unsigned long long* prev_end = acc + KT_SLOTS * 3;
   const int lane = threadIdx.x;
   unsigned long long prev = *prev_end;
-  for (int s = 0; s < KT_SLOTS; ++s) {
+  // slots in the order their kernels run in a pass
+  const int order[KT_SLOTS] = {KT_EC_LOOKUP, KT_C1BITS, KT_CONV1, KT_CONV0, KT_CONV0 + 1, KT_CONV0 + 2, KT_CONV0 + 3, KT_CONV0 + 4,
+                               KT_CONV0 + 5, KT_CONV0 + 6, KT_CONV0 + 7, KT_HEADS, KT_EC_COMMIT, KT_STEP, KT_FOLD, 15};
+  for (int oi = 0; oi < KT_SLOTS; ++oi) {
+    const int s = order[oi];
     unsigned long long* p = kt + (size_t)s * KT_SUB * 2 + 2 * lane;
     unsigned long long st = p[0], en = p[1];
     for (int o = 16; o; o >>= 1) {

@@ -183,12 +183,13 @@ class SelfPlay:
         finally:
             check(lib.a5__debug_ktime_enable(0))
         self.passes += passes + 1
-        names = ["k_c1_bits", "k_tc_conv1m"] + [f"k_tc_conv2[{i}]" for i in range(8)] + ["k_tc_fc", "k_step", "(fold)"]
+        names = ["k_c1_bits", "k_tc_conv1m"] + [f"k_tc_conv2[{i}]" for i in range(8)] + ["k_tc_fc", "k_step", "(fold)",
+                                                                                          "k_ec_lookup", "k_ec_commit"]
         table = {}
-        for i, nm in enumerate(names):
+        for i in [13] + list(range(11)) + [14, 11, 12]:          # slots in the order their kernels run
             cnt = out[3 * i + 2]
             if cnt > 0:
-                table[nm] = (out[3 * i] / cnt / 1000.0, out[3 * i + 1] / cnt / 1000.0)
+                table[names[i]] = (out[3 * i] / cnt / 1000.0, out[3 * i + 1] / cnt / 1000.0)
         if "k_tc_conv2[0]" in table and "k_tc_conv2[1]" not in table:      # one launch for all block convs
             table = {("k_tc_mega" if k == "k_tc_conv2[0]" else k): v for k, v in table.items()}
         return table

@@ -285,7 +285,7 @@ def conv_roofline(kt, S, N, pk, traffic):
     mega = "k_tc_mega" in kt
     conv_flop = 2.0 * CONV_MAC_PER_CELL * C * N
     ach = conv_flop / (conv_us * 1e-6) / 1e12
-    net_us = sum(v[0] for k, v in kt.items() if k not in ("k_step", "(fold)"))
+    net_us = sum(v[0] for k, v in kt.items() if k not in ("k_step", "(fold)", "k_ec_lookup", "k_ec_commit"))
     flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * C / 121) * N
     tr = traffic.get("conv_dram_bytes_per_pass") * N / 4096.0 * (C / 121.0) if traffic else None
     return {"bound": "tensor", "kernel": ("k_tc_mega (the eight block-conv layers as one chunk-major tcgen05 cta_group::2 launch)" if mega else
