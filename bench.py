@@ -287,7 +287,7 @@ def conv_roofline(kt, S, N, pk, traffic):
     ach = conv_flop / (conv_us * 1e-6) / 1e12
     net_us = sum(v[0] for k, v in kt.items() if k not in ("k_step", "(fold)", "k_ec_lookup", "k_ec_commit"))
     flop = FLOP_PER_LEAF.get(S, FLOP_PER_LEAF[11] * C / 121) * N
-    tr = traffic.get("conv_dram_bytes_per_pass") * N / 4096.0 * (C / 121.0) if traffic else None
+    tr = traffic.get("conv_dram_bytes_per_pass") * N / float(traffic.get("boards", 4096)) * (C / 121.0) if traffic else None
     return {"bound": "tensor", "kernel": ("k_tc_mega (the eight block-conv layers as one chunk-major tcgen05 cta_group::2 launch)" if mega else
                                           "k_tc_conv2 (tcgen05 cta_group::2 3x3 conv + residual, 8 launches per pass)"),
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
