@@ -64,6 +64,8 @@ _SIGS = {
     "a5_engine_sims_left": (_P, [_P]),
     "a5_engine_busy": (_I, [_P, C.POINTER(C.c_int32), _P]),
     "a5_engine_finish_move": (_I, [_P, _P, _P, _P]),
+    "a5_engine_collect_moves": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "a5_engine_submit_roots": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "a5_engine_root_stats": (_I, [_P, _P, _P, _P, _P, _P]),
     "a5_engine_node_stats": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "a5_engine_tau": (_P, [_P]),

@@ -889,6 +889,82 @@ __global__ void __launch_bounds__(WPB * 32) k_finish_move(const __grid_constant_
   W.flush();
 }
 
+// Continuous batching of get_action calls (auto_play = 0; a5_engine_collect_moves / a5_engine_submit_roots).
+// The budget rule (player.py:140-143) gives re-used trees fewer simulations, so the searches of a batch end in
+// different passes.  k_collect_moves closes every search that has ended since the last call -- calc_policy
+// (player.py:84-126), utils.step and utils.is_game_over of the played position -- into a compact row and parks the
+// game (active = 0) until k_submit_roots gives it its next root; the other games keep searching in between.
+template <int NCH>
+__global__ void __launch_bounds__(WPB * 32) k_collect_moves(const __grid_constant__ EP P, int cap, int32_t* count, int32_t* game,
+                                                           float* policy, int32_t* action, int8_t* next, int8_t* code) {
+  __shared__ __align__(16) int8_t s_board[WPB][256];
+  __shared__ __align__(16) float s_f[WPB][256];
+  __shared__ uint32_t s_valid[WPB][4 * NCH];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * WPB + wid;
+  if (g >= P.N) return;
+  if (!P.active[g] || P.sims_left[g] > 0 || P.need_eval[g]) return;
+  int row = 0;
+  if (lane == 0) row = atomicAdd(count, 1);
+  row = __shfl_sync(FULL, row, 0);
+  if (row >= cap) return;                                  // no room this time: the search stays closed-but-uncollected
+  Warp<NCH> W(P, g, lane, s_board[wid], s_f[wid]);
+  warp_valid_masks<NCH>(P.S, P.goal, lane, s_valid[wid]);
+  int8_t* sb = W.sb;
+  for (int c = lane; c < P.KB; c += 32) sb[c] = P.root_board[(size_t)g * P.KB + c];
+  __syncwarp();
+  uint32_t own[NCH], opp[NCH];
+  W.board_masks(own, opp);
+  int ep;
+  const int idx = W.find(W.hash_masks(own, opp), own, opp, &ep);
+  const int a = W.move_policy(idx >= 0 ? W.node(idx) : nullptr, policy + (size_t)row * P.C);
+  __syncwarp();
+  if (a >= 0) warp_step(sb, P.C, a, lane);
+  __syncwarp();
+  W.board_masks(own, opp);
+  const int cd = warp_terminal_bits<NCH>(own, opp, s_valid[wid], P.S, P.goal, lane);
+  for (int c = lane; c < P.C; c += 32) next[(size_t)row * P.C + c] = sb[c];
+  if (lane == 0) {
+    game[row] = g;
+    action[row] = a;
+    code[row] = (int8_t)cd;
+    P.active[g] = 0;
+  }
+  W.st[0] += 1;
+  W.flush();
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(WPB * 32) k_submit_roots(const __grid_constant__ EP P, int n, const int32_t* game,
+                                                          const int8_t* boards, const int32_t* last, const uint8_t* clr) {
+  __shared__ __align__(16) int8_t s_board[WPB][256];
+  __shared__ __align__(16) float s_f[WPB][256];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WPB + wid;
+  if (row >= n) return;
+  const int g = game[row];
+  if (g < 0 || g >= P.N) return;
+  Warp<NCH> W(P, g, lane, s_board[wid], s_f[wid]);
+  if (clr && clr[row]) {
+    W.clear_table();
+    if (lane == 0) P.tau[g] = P.init_temp;
+  }
+  int8_t* sb = W.sb;
+  for (int c = lane; c < P.KB; c += 32) sb[c] = c < P.C ? boards[(size_t)row * P.C + c] : 0;
+  __syncwarp();
+  for (int c = lane; c < P.KB; c += 32) P.root_board[(size_t)g * P.KB + c] = sb[c];
+  uint32_t own[NCH], opp[NCH];
+  W.board_masks(own, opp);
+  W.collect(own, opp);
+  const int b = W.budget_for_root(own, opp);
+  if (lane == 0) {
+    P.active[g] = 1; P.need_eval[g] = 0; P.depth[g] = 0;
+    P.root_last[g] = last ? last[row] : -1;
+    P.sims_left[g] = b;
+  }
+  W.flush();
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(WPB * 32) k_node_stats(const __grid_constant__ EP P, const int8_t* boards, int32_t* dn,
                                                         float* dw, float* dp, int32_t* dsum) {
@@ -1194,6 +1270,25 @@ int a5_engine_finish_move(a5_engine* e, float* d_policy, int32_t* d_action, void
   A5_ARG(e);
   if (e->p.auto_play) { set_error("a5_engine_finish_move: engine is in auto_play mode"); return A5_ERR_STATE; }
   DISPATCH(k_finish_move, ngrid(e), WPB * 32, (cudaStream_t)stream, e->p, d_policy, d_action);
+  return A5_OK;
+}
+
+int a5_engine_collect_moves(a5_engine* e, int cap, int32_t* d_count, int32_t* d_game, float* d_policy, int32_t* d_action,
+                            int8_t* d_next, int8_t* d_code, void* stream) {
+  A5_ARG(e && cap > 0 && d_count && d_game && d_policy && d_action && d_next && d_code);
+  if (e->p.auto_play) { set_error("a5_engine_collect_moves: engine is in auto_play mode"); return A5_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  A5_CUDA(cudaMemsetAsync(d_count, 0, 4, st));
+  DISPATCH(k_collect_moves, ngrid(e), WPB * 32, st, e->p, cap, d_count, d_game, d_policy, d_action, d_next, d_code);
+  return A5_OK;
+}
+
+int a5_engine_submit_roots(a5_engine* e, int n, const int32_t* d_game, const int8_t* d_boards, const int32_t* d_last,
+                           const uint8_t* d_clear, void* stream) {
+  A5_ARG(e && n >= 0 && (n == 0 || (d_game && d_boards)));
+  if (e->p.auto_play) { set_error("a5_engine_submit_roots: engine is in auto_play mode"); return A5_ERR_STATE; }
+  if (n == 0) return A5_OK;
+  DISPATCH(k_submit_roots, (n + WPB - 1) / WPB, WPB * 32, (cudaStream_t)stream, e->p, n, d_game, d_boards, d_last, d_clear);
   return A5_OK;
 }
 

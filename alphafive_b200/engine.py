@@ -132,6 +132,18 @@ class SearchEngine:
         check(self.lib.a5_engine_finish_move(self.handle, ptr(policy), ptr(action), stream_ptr()))
         return policy, action
 
+    def collect_moves(self, cap, count, game, policy, action, nxt, code):
+        """a5_engine_collect_moves into caller-owned device buffers (see include/alphafive.h): every search that has
+        ended since the last call -> compact rows (game, calc_policy row, action, next position, terminal code);
+        those games are parked until submit_roots gives them their next root."""
+        check(self.lib.a5_engine_collect_moves(self.handle, int(cap), ptr(count), ptr(game), ptr(policy), ptr(action),
+                                               ptr(nxt), ptr(code), stream_ptr()))
+
+    def submit_roots(self, n, game, boards, last=None, clear=None):
+        """a5_engine_submit_roots: Player.get_action entry for the n games listed in ``game`` (device tensors);
+        every other game is left as it is."""
+        check(self.lib.a5_engine_submit_roots(self.handle, int(n), ptr(game), ptr(boards), ptr(last), ptr(clear), stream_ptr()))
+
     def root_stats(self):
         n = torch.empty((self.N, self.C), dtype=torch.int32, device=self.device)
         w = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
@@ -182,6 +194,43 @@ class SearchEngine:
         cnt, games = C.c_int32(), C.c_int32()
         check(self.lib.a5_engine_harvest(self.handle, ptr(buf), buf.shape[0], C.byref(cnt), C.byref(games), stream_ptr()))
         return buf[:cnt.value], games.value
+
+    def replay_passes(self, k: int, net, cache=None, net_mode=None):
+        """``k`` search passes back to back on the current stream (leaf evaluation by the on-device ``net`` +
+        tree pass; through ``cache``, a selfplay.EvalCache, when given).  The pass is captured into a CUDA graph
+        the first time (keyed on net, compute path, engine parameter version and cache) and replayed afterwards,
+        which keeps the launch gaps off the GPU; no host synchronisation once the graph exists."""
+        if self._prob is None:
+            self._prob = torch.empty((self.N, self.C), dtype=torch.float32, device=self.device)
+            self._value = torch.empty((self.N,), dtype=torch.float32, device=self.device)
+        prob, value = self._prob, self._value
+        if cache is not None and cache.net_version != net.version:
+            cache.clear()                             # cached results belong to one set of weights
+            cache.net_version = net.version
+
+        def one_pass():
+            if cache is not None:
+                self.cached_pass(net, cache, prob, value, net_mode)
+            else:
+                net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
+                self.step(prob, value)
+
+        key = (id(net), net_mode, self._version, id(cache))
+        if self.use_graph and k >= 4 and self._graph_key != key:
+            # one eager pass (counts), then capture the pass
+            one_pass()
+            k -= 1
+            torch.cuda.current_stream().synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                one_pass()
+            self._graph_key = key
+        if self.use_graph and self._graph_key == key:
+            for _ in range(k):
+                self._graph.replay()
+        else:
+            for _ in range(k):
+                one_pass()
 
     # -- convenience: run until every game's budget is spent (auto_play = 0) ------
     def run_search(self, net=None, pv_fn=None, check_every: int = 16, net_mode=None, active=None, cache=None):
@@ -237,33 +286,7 @@ class SearchEngine:
                     if self.busy() == 0:
                         break
                     continue
-                if cache is not None and cache.net_version != net.version:
-                    cache.clear()                             # cached results belong to one set of weights
-                    cache.net_version = net.version
-
-                def one_pass():
-                    if cache is not None:
-                        self.cached_pass(net, cache, prob, value, net_mode)
-                    else:
-                        net.forward_raw(self.planes_ptr, self.N, prob, value, net_mode)
-                        self.step(prob, value)
-
-                key = (id(net), net_mode, self._version, id(cache))
-                if self.use_graph and left >= 4 and self._graph_key != key:
-                    # one eager pass (counts), then capture the pass; replays keep the launch gaps off the GPU
-                    one_pass()
-                    left -= 1
-                    torch.cuda.current_stream().synchronize()
-                    self._graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self._graph):
-                        one_pass()
-                    self._graph_key = key
-                if self.use_graph and self._graph_key == key:
-                    for _ in range(left):
-                        self._graph.replay()
-                else:
-                    for _ in range(left):
-                        one_pass()
+                self.replay_passes(left, net, cache, net_mode)
                 if self.busy() == 0:
                     break
                 continue

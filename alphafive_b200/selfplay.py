@@ -335,6 +335,82 @@ class BatchedPlayer:
         return pol, self.h_action.numpy()
 
 
+    # ---- continuous batching: searches are collected as they end, the other players keep searching -----------
+    def start_stream(self, boards, last, clear=None, passes=4, cap=None):
+        """Continuous form of ``get_actions``.  The budget rule (player.py:140-143) gives re-used trees fewer
+        simulations, so the searches of a batch end in different passes; ``get_actions`` returns when the slowest is
+        done, the reference's players are independent objects and never wait for each other.  Here every player gets
+        its root (host arrays as in ``get_actions``), then the caller alternates
+
+            games, policy, action, nxt, codes = bp.poll()      # searches that have ended (host arrays)
+            bp.submit(games, next_boards, last, clear)         # their next roots (host arrays)
+
+        ``poll`` queues ``passes`` search passes before it waits for its results, so the device never idles while
+        the host decides; a collected player is parked until its next root arrives.  Per-player results are those
+        of ``get_actions`` (every game owns its table and its counter-based RNG stream)."""
+        N, S, C = self.N, self.S, self.C
+        dev = self.engine.device
+        cap = int(cap or max(64, N // 16))
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+        dv = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+        self._s = dict(
+            cap=cap, passes=int(passes), ev=torch.cuda.Event(), sub_ev=None,
+            d_count=dv(1, dtype=torch.int32), d_game=dv(cap, dtype=torch.int32), d_policy=dv(cap, C, dtype=torch.float32),
+            d_action=dv(cap, dtype=torch.int32), d_next=dv(cap, C, dtype=torch.int8), d_code=dv(cap, dtype=torch.int8),
+            h_count=pin(1, dtype=torch.int32), h_game=pin(cap, dtype=torch.int32), h_policy=pin(cap, C, dtype=torch.float32),
+            h_action=pin(cap, dtype=torch.int32), h_next=pin(cap, C, dtype=torch.int8), h_code=pin(cap, dtype=torch.int8),
+            s_game=pin(N, dtype=torch.int32), s_boards=pin(N, C, dtype=torch.int8), s_last=pin(N, dtype=torch.int32),
+            s_clear=pin(N, dtype=torch.uint8),
+            sd_game=dv(N, dtype=torch.int32), sd_boards=dv(N, C, dtype=torch.int8), sd_last=dv(N, dtype=torch.int32),
+            sd_clear=dv(N, dtype=torch.uint8), h2d=0, d2h=0, polls=0)
+        self.h_boards.copy_(torch.as_tensor(boards, dtype=torch.int8).reshape(N, S, S))
+        self.h_last.copy_(torch.as_tensor(last, dtype=torch.int32))
+        self.d_boards.copy_(self.h_boards, non_blocking=True)
+        self.d_last.copy_(self.h_last, non_blocking=True)
+        self._s["h2d"] += N * C + 4 * N
+        self.engine.set_roots(self.d_boards, self.d_last, None, clear)
+        self.engine.step()                                   # first descent: every game reaches its root
+
+    def poll(self):
+        """-> (games int32[n], policy f32[n,S,S], action int32[n], next int8[n,S,S], codes int8[n]): the searches
+        that have ended since the last poll (at most ``cap`` of them; the rest comes with the next one)."""
+        s = self._s
+        self.engine.collect_moves(s["cap"], s["d_count"], s["d_game"], s["d_policy"], s["d_action"], s["d_next"], s["d_code"])
+        for k in ("count", "game", "policy", "action", "next", "code"):
+            s["h_" + k].copy_(s["d_" + k], non_blocking=True)
+        s["ev"].record()
+        self.engine.replay_passes(s["passes"], self.net, self.cache)     # the device works on while the host waits / decides
+        s["ev"].synchronize()
+        n = min(int(s["h_count"][0]), s["cap"])
+        s["d2h"] += sum(s["h_" + k].numel() * s["h_" + k].element_size() for k in ("count", "game", "policy", "action", "next", "code"))
+        s["polls"] += 1
+        return (s["h_game"][:n].numpy().copy(), s["h_policy"][:n].numpy().reshape(n, self.S, self.S).copy(),
+                s["h_action"][:n].numpy().copy(), s["h_next"][:n].numpy().reshape(n, self.S, self.S).copy(),
+                s["h_code"][:n].numpy().copy())
+
+    def submit(self, games, boards, last, clear=None):
+        """Next roots of the players ``games`` (host arrays: boards int8[n,S,S], last int32[n], clear uint8[n])."""
+        s = self._s
+        n = len(games)
+        if n == 0:
+            return
+        if s["sub_ev"] is not None:
+            s["sub_ev"].synchronize()                        # the staging buffers of the previous submit are free again
+        s["s_game"][:n].copy_(torch.as_tensor(games, dtype=torch.int32))
+        s["s_boards"][:n].copy_(torch.as_tensor(boards, dtype=torch.int8).reshape(n, self.C))
+        s["s_last"][:n].copy_(torch.as_tensor(last, dtype=torch.int32))
+        if clear is None:
+            s["s_clear"][:n].zero_()
+        else:
+            s["s_clear"][:n].copy_(torch.as_tensor(clear, dtype=torch.uint8))
+        for k in ("game", "boards", "last", "clear"):
+            s["sd_" + k][:n].copy_(s["s_" + k][:n], non_blocking=True)
+        s["h2d"] += n * (4 + self.C + 4 + 1)
+        self.engine.submit_roots(n, s["sd_game"], s["sd_boards"], s["sd_last"], s["sd_clear"])
+        s["sub_ev"] = torch.cuda.Event()
+        s["sub_ev"].record()
+
+
 class PipelinedBatchedPlayer(BatchedPlayer):
     """``BatchedPlayer`` with the search of the two halves of the batch pipelined on SM-partitioned streams
     (alphafive_b200.pipeline); same call, same host buffers, same results."""

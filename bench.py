@@ -10,9 +10,11 @@ the harvest of the finished games, the all-gather of their records over NCCL (N 
 overlapped with the next step's passes) and their push into the device-resident RandomStack (the sink of
 main.py:60-64) on every rank.
 `value` is whole-job moves/s with everything resident in HBM (games are played, recorded
-and restarted on the device); `e2e` is the same metric through the host-buffer API
-(BatchedPlayer.get_actions: H2D boards, search, D2H policies/actions/next boards each
-move) over --steps consecutive moves of a steady-state mix of positions.  The other BASELINE
+and restarted on the device); `e2e` is the same metric through the host-buffer API over a steady-state
+mix of positions: BatchedPlayer.start_stream / poll / submit -- the searches that have ended are read back
+to the host (policies, actions, next boards), the host sends the next roots, the other players keep
+searching -- for max(--steps, 8) moves per player; `e2e.lockstep_call` is the one-move-of-every-player
+call (BatchedPlayer.get_actions), which returns when the slowest search is done.  The other BASELINE
 configurations (15x15 / 800 sims, the arena, a single game) are reported under `configs`.
 One JSON line on stdout (rank 0).
 """
@@ -46,7 +48,9 @@ def parse():
     ap.add_argument("--upper", type=int, default=None)
     ap.add_argument("--net-mode", default=os.environ.get("A5_NET_MODE", "auto"), choices=["auto", "fp32", "tc"])
     ap.add_argument("--e2e-steps", type=int, default=None,
-                    help="timed get_actions calls of the end-to-end leg (default: max(--steps, 8); 0 disables it)")
+                    help="moves per player timed in the end-to-end leg (default: max(--steps, 8); 0 disables it)")
+    ap.add_argument("--stream-passes", type=int, default=4, help="search passes queued per poll of the continuous e2e leg")
+    ap.add_argument("--lockstep-calls", type=int, default=3, help="timed BatchedPlayer.get_actions calls (secondary e2e figure)")
     ap.add_argument("--preroll-moves", type=int, default=48,
                     help="untimed moves at --preroll-sims before the warm-up, so games are spread over all plies")
     ap.add_argument("--preroll-sims", type=int, default=40)
@@ -57,9 +61,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--eval-cache", type=int, default=int(os.environ.get("A5_EVAL_CACHE", "1")),
                     help="1: cross-game evaluation cache + compact leaf batch in the lock-step self-play runs (a5_evalcache_*); "
-                         "2: also in the end-to-end BatchedPlayer leg (there every search of a call starts together, demand "
-                         "exceeds the compact batch in some calls and the stragglers cost what the smaller forward gains: "
-                         "measured equal on average, profiles/r02_evalcache.txt); 0: off")
+                         "it is shared with the continuous end-to-end leg; 2: also in the lock-step get_actions calls (there every "
+                         "search of a call starts together, demand exceeds the compact batch in some calls and the stragglers "
+                         "cost what the smaller forward gains: measured equal on average, profiles/r02_evalcache.txt); 0: off")
     return ap.parse_args()
 
 
@@ -327,6 +331,18 @@ def measured_traffic():
         return None
 
 
+def desync_budgets(engine, sims, seed):
+    """Spread the phases of the searches uniformly: every game's *current* move gets a remaining budget drawn from
+    [1, sims] (warm-up only).  Without it all games switch to the full budget in the same pass after the preroll (or
+    start their first search together in the end-to-end leg), finish their moves in waves sims passes apart, and
+    the number of moves inside the timed window depends on where its edges fall between two waves (+-2 %)."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(int(seed))
+    sl = engine.sims_left()
+    sl.copy_(torch.minimum(sl, torch.randint(1, sims + 1, sl.shape, device=sl.device, dtype=torch.int32, generator=g)))
+
+
 # --------------------------------------------------------------------------------------
 def run_ours(a):
     import numpy as np
@@ -405,6 +421,8 @@ def run_ours(a):
         sp.run_passes(a.preroll_moves * a.preroll_sims)
         sp.harvest()
         sp.set_budget(sims, upper)
+        sp.run_passes(a.preroll_sims + 12)                    # every game has started a move with the full budget
+        desync_budgets(sp.engine, sims, 1234 + rank)
     for _ in range(a.warmup):
         one_step()
     drain_sink()
@@ -452,6 +470,7 @@ def run_ours(a):
     # tables, then time consecutive moves: tree reuse, budget cuts, terminal positions and restarts included.
     e2e_steps = a.e2e_steps if a.e2e_steps is not None else max(a.steps, 8)
     d_boards, d_last = sp.engine.roots()
+    tau0 = sp.engine.tau().clone()                           # every game's temperature (Player.tau): the end-to-end legs resume these games
     boards, last = d_boards.cpu().numpy(), d_last.cpu().numpy()
     occupancy = stack.count / stack.length
     cache_info = None
@@ -468,15 +487,70 @@ def run_ours(a):
     sp.engine.close()
     del sp, stack, bufs
     torch.cuda.empty_cache()
-    e2e_val, e2e_calls, bp_bytes, e2e_cache = None, [], (0, 0), None
+    e2e_val, e2e_calls, bp_bytes, e2e_cache, e2e_stream = None, [], (0, 0), None, None
     if e2e_steps > 0:
+        # (1) continuous batching (BatchedPlayer.start_stream / poll / submit): every search that has ended is read
+        # back, stepped on the host side of the API and re-rooted while the others keep searching -- the headline e2e.
+        bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
+                           eval_cache=shared_cache if shared_cache is not None else False,
+                           board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
+        bp.start_stream(boards, last, np.ones(N, np.uint8), passes=a.stream_passes, cap=int(os.environ.get('A5_STREAM_CAP', '0')) or None)
+        bp.engine.tau().copy_(tau0)                              # Player.tau of the resumed games (a fresh Player starts at init_temp)
+        desync_budgets(bp.engine, sims, 4321 + rank)             # (first search of every player only)
+
+        def stream_until(target):
+            got = 0
+            while got < target:
+                games, pol, act, nxt, codes = bp.poll()
+                over = codes != 0
+                bp.submit(games, np.where(over[:, None, None], 0, nxt).astype(np.int8), np.where(over, -1, act).astype(np.int32),
+                          over.astype(np.uint8))                 # a finished game restarts: Player.reset() (player.py:73)
+                got += len(games)
+            return got
+
+        stream_until(2 * N)                                      # warm-up: tables built, budgets desynchronised
+        st0 = bp.cache.stats() if bp.cache is not None else None
+        b0 = (bp._s["h2d"], bp._s["d2h"], bp._s["polls"])
+        ec0 = bp.engine.counters()
+        barrier()
+        t0 = time.perf_counter()
+        got = stream_until(e2e_steps * N)
+        t_stream = time.perf_counter() - t0
+        barrier()
+        tt = torch.tensor([t_stream, float(got)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmx = tt.clone(); dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+            tsm = tt.clone(); dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
+            t_stream, got_all = tmx[0].item(), tsm[1].item()
+        else:
+            got_all = float(got)
+        e2e_val = got_all / t_stream
+        polls = bp._s["polls"] - b0[2]
+        ec1 = bp.engine.counters()
+        steps_equiv = max(1e-9, got / N)                         # one "step" = N moves, as in the lock-step call
+        e2e_stream = {"moves": got_all, "seconds": t_stream, "polls": polls, "passes_per_poll": a.stream_passes,
+                      "collect_cap": bp._s["cap"], "moves_per_poll": got / max(1, polls),
+                      "sims_per_move": (ec1["sims"] - ec0["sims"]) / max(1, ec1["moves"] - ec0["moves"]),
+                      "passes_per_move_per_player": N * polls * a.stream_passes / max(1, got),
+                      "h2d_bytes_per_step": (bp._s["h2d"] - b0[0]) / steps_equiv, "d2h_bytes_per_step": (bp._s["d2h"] - b0[1]) / steps_equiv}
+        if bp.cache is not None:
+            st = bp.cache.stats()
+            lk = max(1, st["lookups"] - st0["lookups"])
+            e2e_cache = {"lookups": lk, "hit_rate": (st["hits"] - st0["hits"]) / lk, "deferred_rate": (st["deferred"] - st0["deferred"]) / lk}
+        bp.engine.close()
+        del bp
+        torch.cuda.empty_cache()
+        # (2) the lock-step call (BatchedPlayer.get_actions): one call = one move of every player, returns when the
+        # slowest search is done
         bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
                            eval_cache=shared_cache if (shared_cache is not None and a.eval_cache >= 2) else False,
                            board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
         bp_bytes = (bp.h2d_bytes, bp.d2h_bytes)
-        clear = np.ones(N, np.uint8)
-        for k in range(max(1, min(a.warmup, 2)) + e2e_steps):
-            timed = k >= max(1, min(a.warmup, 2))
+        bp.engine.tau().copy_(tau0)
+        clear = np.zeros(N, np.uint8)                        # fresh engine: the tables are empty, tau is the resumed games'
+        n_calls = max(2, min(e2e_steps, a.lockstep_calls))
+        for k in range(2 + n_calls):
+            timed = k >= 2
             barrier()
             t0 = time.perf_counter()
             pol, act, nxt, codes = bp.get_actions(boards, last, None, clear, advance=True)
@@ -490,11 +564,7 @@ def run_ours(a):
         e2e_t = torch.tensor([sum(e2e_calls)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_val = N * world * len(e2e_calls) / e2e_t.item()
-        if bp.cache is not None:
-            st = bp.cache.stats()
-            e2e_cache = {"lookups": st["lookups"] - cache_info["lookups"], "hit_rate": (st["hits"] - cache_info["_hits"]) / max(1, st["lookups"] - cache_info["lookups"]),
-                         "deferred_rate": (st["deferred"] - cache_info["_deferred"]) / max(1, st["lookups"] - cache_info["lookups"])}
+        e2e_lock = N * world * len(e2e_calls) / e2e_t.item()
         bp.engine.close()
         del bp
         torch.cuda.empty_cache()
@@ -518,13 +588,23 @@ def run_ours(a):
                        "l2": "per-pass working set (activations + node arenas) exceeds the 126 MB L2",
                        "cuda_graph": not a.no_graph, "step": f"{sims} lock-step passes + harvest + record all-gather + RandomStack push",
                        "schedule": "single stream, CUDA-graph replay of one pass; record gather + replay-buffer push on a side stream",
-                       "preroll": f"{a.preroll_moves} untimed moves at {a.preroll_sims} sims to spread games over all plies"},
-            "e2e": {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": bp_bytes[0], "d2h_bytes_per_step": bp_bytes[1],
-                    "api": "BatchedPlayer.get_actions(host boards) + device step/terminal, consecutive moves from the "
-                           "lock-step run's positions (tree reuse, budget rule, restarts)",
-                    "calls": len(e2e_calls), "seconds": sum(e2e_calls),
-                    "moves_per_s_min": N * world / max(e2e_calls) if e2e_calls else None,
-                    "moves_per_s_max": N * world / min(e2e_calls) if e2e_calls else None},
+                       "preroll": f"{a.preroll_moves} untimed moves at {a.preroll_sims} sims to spread games over all plies, then the "
+                                  "remaining budgets of the moves in progress are drawn uniformly so that the searches end at "
+                                  "uniformly spread passes (no waves of moves across the timed window's edges)"},
+            "e2e": ({"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": e2e_stream["h2d_bytes_per_step"],
+                     "d2h_bytes_per_step": e2e_stream["d2h_bytes_per_step"],
+                     "api": "BatchedPlayer.start_stream / poll / submit (continuous batching over a5_engine_collect_moves / "
+                            "a5_engine_submit_roots): the searches that have ended are read back to the host (policy, action, "
+                            "next position, terminal code), the host restarts finished games and sends the next roots, the other "
+                            "players keep searching; positions from the lock-step run (tree reuse, budget rule, restarts); one "
+                            "step = as many moves as there are players",
+                     "stream": e2e_stream,
+                     "lockstep_call": {"value": e2e_lock, "unit": "moves/s", "h2d_bytes_per_step": bp_bytes[0], "d2h_bytes_per_step": bp_bytes[1],
+                                       "api": "BatchedPlayer.get_actions(host boards) + device step/terminal: one move of every player "
+                                              "per call, returns when the slowest search is done",
+                                       "calls": len(e2e_calls), "seconds": sum(e2e_calls),
+                                       "moves_per_s_min": N * world / max(e2e_calls), "moves_per_s_max": N * world / min(e2e_calls)}}
+                    if e2e_stream is not None else {"value": None, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}),
             "gpu_launches": int(passes_timed * launches_per_pass),
             "ms_per_pass": ms / max(1.0, passes_timed),
             "moves": moves, "sims_run": nsims, "games_finished": games,
@@ -615,6 +695,8 @@ def run_configs(a, rank, world, net11, mode):
         sp.run_passes(32 * 40)
         sp.harvest()
         sp.set_budget(sims, upper)
+        sp.run_passes(52)
+        desync_budgets(sp.engine, sims, 99 + rank)
         sp.run_passes(sims)                                   # warm-up step
         sp.harvest()
         c0 = sp.counters()

@@ -145,6 +145,25 @@ int a5_engine_busy(a5_engine* e, int32_t* h_busy, void* stream);
  * None), d_action int32[N] flat cell. */
 int a5_engine_finish_move(a5_engine* e, float* d_policy, int32_t* d_action, void* stream);
 
+/* Continuous batching of get_action calls (auto_play = 0).  The budget rule (player.py:140-143) gives
+ * re-used trees fewer simulations, so the searches of a batch end in different passes; the reference's
+ * players are independent objects and none of them waits for another (each worker of main.py:50-55 calls
+ * get_action on its own).  a5_engine_collect_moves closes every search that has ended and has not been
+ * collected yet -- Player.calc_policy (player.py:84-126), then utils.step (utils.py:275-283) and
+ * utils.is_game_over (utils.py:199-235) of the played position -- into compact rows:
+ *   d_count int32[1] searches found (may exceed cap: the rest is returned by the next call),
+ *   d_game int32[cap] game index, d_policy f32[cap][S*S], d_action int32[cap] flat cell,
+ *   d_next int8[cap][S*S] position after the move (side to move = +1), d_code int8[cap] its terminal code
+ *   (a5_rules_terminal).  A collected game is parked (not searched) until
+ * a5_engine_submit_roots gives it its next root: Player.get_action entry for game d_game[i] with board
+ * d_boards[i] (int8[n][S*S]), d_last[i] (flat cell or -1; NULL = none) and, where d_clear[i] != 0,
+ * Player.reset() first (d_clear may be NULL).  All other games are left untouched and keep searching.
+ * d_game must not name a game twice. */
+int a5_engine_collect_moves(a5_engine* e, int cap, int32_t* d_count, int32_t* d_game, float* d_policy,
+                            int32_t* d_action, int8_t* d_next, int8_t* d_code, void* stream);
+int a5_engine_submit_roots(a5_engine* e, int n, const int32_t* d_game, const int8_t* d_boards,
+                           const int32_t* d_last, const uint8_t* d_clear, void* stream);
+
 /* Root node statistics of every game as dense per-cell arrays (parity tests, GUI):
  * n int32[N][S*S], w f32, p f32, sum_n int32[N]; any pointer may be NULL. */
 int a5_engine_root_stats(a5_engine* e, int32_t* d_n, float* d_w, float* d_p, int32_t* d_sum_n, void* stream);
