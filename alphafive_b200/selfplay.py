@@ -350,7 +350,7 @@ class BatchedPlayer:
         of ``get_actions`` (every game owns its table and its counter-based RNG stream)."""
         N, S, C = self.N, self.S, self.C
         dev = self.engine.device
-        cap = int(cap or max(64, N // 16))
+        cap = int(cap or max(64, N // 32))       # rows per poll: ~4 x the mean arrivals at 4 passes per poll and ~500 sims
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
         dv = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
         self._s = dict(
