@@ -43,7 +43,7 @@ struct EP {
   unsigned long long* rng_ctr;
   double* tau;
   int32_t *serial, *rec_len;
-  int8_t* rec_board; float* rec_policy; int32_t* rec_last;
+  uint8_t* rec_stage;           // [game][ply][rec_stride]: the plies of the game in progress, already in record layout
   uint8_t* out_rec; int32_t* out_count;
   long long* gstat;
   int8_t* planes;
@@ -616,26 +616,37 @@ struct Warp {
     if (lane == 0) wsum = np_sum(sf, L);
     wsum = __shfl_sync(FULL, wsum, 0);
     const int result = (value == 0.0f && code == 3) ? 0 : ((L & 1) ? 1 : -1);
-    const int8_t* rb = P.rec_board + (size_t)g * P.C * P.KB;
-    const float* rp = P.rec_policy + (size_t)g * P.C * P.C;
-    const int32_t* rl = P.rec_last + (size_t)g * P.C;
-    for (int t = 0; t < L; ++t) {
-      uint8_t* out = P.out_rec + (size_t)(base + t) * P.rec_stride;
-      if (lane == 0) {
-        a5_record_header* hd = (a5_record_header*)out;
-        hd->game_id = P.gid_base + g;
-        hd->game_serial = P.serial[g];
-        hd->ply = (int16_t)t;
-        hd->game_len = (int16_t)L;
-        hd->last_action = rl[t];
-        hd->value = (t & 1) ? -value : value;
-        hd->weight = __fdiv_rn(__fmul_rn((float)L, sf[t]), wsum);
-        hd->result = result;
+    // the plies were staged in record layout as they were played (board, policy, last_action): complete the
+    // headers, lane = ply, then move the L records as one linear 16-byte-vector copy with four loads in flight per
+    // lane (the per-ply, per-field loop this replaces was the slowest warp of every pass in which a game ended)
+    uint8_t* stage = P.rec_stage + (size_t)g * P.C * P.rec_stride;
+    const int serial = P.serial[g];
+    for (int t = lane; t < L; t += 32) {
+      a5_record_header* hd = (a5_record_header*)(stage + (size_t)t * P.rec_stride);
+      hd->game_id = P.gid_base + g;
+      hd->game_serial = serial;
+      hd->ply = (int16_t)t;
+      hd->game_len = (int16_t)L;
+      hd->value = (t & 1) ? -value : value;
+      hd->weight = __fdiv_rn(__fmul_rn((float)L, sf[t]), wsum);
+      hd->result = result;
+    }
+    __syncwarp();
+    const uint4* src = (const uint4*)stage;
+    uint4* dst = (uint4*)(P.out_rec + (size_t)base * P.rec_stride);
+    const int n = L * (P.rec_stride / 16);
+    for (int i0 = 0; i0 < n; i0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i < n) v[u] = src[i];
       }
-      int8_t* ob = (int8_t*)(out + sizeof(a5_record_header));
-      for (int c = lane; c < P.rec_bb; c += 32) ob[c] = c < P.C ? rb[(size_t)t * P.KB + c] : 0;
-      float* op = (float*)(out + sizeof(a5_record_header) + P.rec_bb);
-      for (int c = lane; c < P.C; c += 32) op[c] = rp[(size_t)t * P.C + c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i < n) dst[i] = v[u];
+      }
     }
     __syncwarp();
   }
@@ -702,11 +713,12 @@ __device__ __forceinline__ void step_body(const EP& P, const float* __restrict__
       int ep;
       int ridx = W.find(W.hash_masks(own, opp), own, opp, &ep);
       int L = P.rec_len[g];
-      float* pol = P.rec_policy + ((size_t)g * P.C + L) * P.C;
+      uint8_t* rs = P.rec_stage + ((size_t)g * P.C + L) * P.rec_stride;       // this ply's record (player.py:65)
+      float* pol = (float*)(rs + sizeof(a5_record_header) + P.rec_bb);
       int action = W.move_policy(ridx >= 0 ? W.node(ridx) : nullptr, pol);
-      int8_t* rbd = P.rec_board + ((size_t)g * P.C + L) * P.KB;
+      int8_t* rbd = (int8_t*)(rs + sizeof(a5_record_header));
       for (int c = lane; c < P.KB; c += 32) rbd[c] = sb[c];
-      if (lane == 0) P.rec_last[(size_t)g * P.C + L] = P.root_last[g];
+      if (lane == 0) ((a5_record_header*)rs)->last_action = P.root_last[g];
       ++L;
       __syncwarp();
       warp_step(sb, P.C, action, lane);
@@ -735,6 +747,7 @@ __device__ __forceinline__ void step_body(const EP& P, const float* __restrict__
       int8_t* rbw = P.root_board + (size_t)g * P.KB;
       for (int c = lane; c < P.KB; c += 32) rbw[c] = sb[c];
       __syncwarp();
+      if (code) break;      // the warp that closed a game is the slowest of its pass: the new game's first descent waits a pass
       continue;
     }
     if (inner >= P.max_inner) break;                // yield: no leaf this pass
@@ -1147,7 +1160,7 @@ int a5_engine_create(const a5_config* cfg, a5_engine** out) {
   size_t o_ctr = take(N * 8), o_tau = take(N * 8);
   size_t o_ser = take(N * 4), o_rlen = take(N * 4);
   size_t recN = p.auto_play ? N : 1;
-  size_t o_rbd = take(recN * p.C * p.KB), o_rpol = take(recN * p.C * p.C * 4), o_rlast = take(recN * p.C * 4);
+  size_t o_rst = take(recN * p.C * (size_t)p.rec_stride);
   size_t o_out = take((size_t)p.rec_cap * p.rec_stride), o_oc = take(16);
   size_t o_gs = take(N * GS * 8);
   size_t o_pl = take(N * 3 * p.C);
@@ -1168,7 +1181,7 @@ int a5_engine_create(const a5_config* cfg, a5_engine** out) {
   p.path = (uint32_t*)(b + o_path);
   p.rng_ctr = (unsigned long long*)(b + o_ctr); p.tau = (double*)(b + o_tau);
   p.serial = (int32_t*)(b + o_ser); p.rec_len = (int32_t*)(b + o_rlen);
-  p.rec_board = (int8_t*)(b + o_rbd); p.rec_policy = (float*)(b + o_rpol); p.rec_last = (int32_t*)(b + o_rlast);
+  p.rec_stage = b + o_rst;
   p.out_rec = b + o_out; p.out_count = (int32_t*)(b + o_oc);
   p.gstat = (long long*)(b + o_gs);
   p.planes = (int8_t*)(b + o_pl);

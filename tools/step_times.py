@@ -17,11 +17,15 @@ sp = SelfPlay(None, n_games=N, net=net, training=True, seed=0, use_graph=False, 
               simulation_per_step=sims, upper_simulation_per_step=sims + 142)
 sp.start()
 sp.set_budget(40, 50); sp.run_passes(48 * 40); sp.harvest(); sp.set_budget(sims, sims + 142)
+sp.run_passes(52)
+g = torch.Generator(device="cuda"); g.manual_seed(7)
+sl = sp.engine.sims_left()
+sl.copy_(torch.minimum(sl, torch.randint(1, sims + 1, sl.shape, device=sl.device, dtype=torch.int32, generator=g)))   # spread the phases (bench.desync_budgets)
 sp.run_passes(sims + 137)
 check(fn(1, None))
 buf = np.zeros((2, 8192), np.uint64)
 tot = []
-for rep in range(8):
+for rep in range(int(sys.argv[3]) if len(sys.argv) > 3 else 8):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     net.forward_raw(sp.engine.planes_ptr, N, sp.prob, sp.value)
     e0.record(); sp.engine.step(sp.prob, sp.value); e1.record()
