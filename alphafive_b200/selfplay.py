@@ -388,6 +388,11 @@ class BatchedPlayer:
                 s["h_action"][:n].numpy().copy(), s["h_next"][:n].numpy().reshape(n, self.S, self.S).copy(),
                 s["h_code"][:n].numpy().copy())
 
+    def stream_stats(self) -> dict:
+        """Bytes copied host->device / device->host and polls since ``start_stream`` (what bench.py reports)."""
+        s = self._s
+        return dict(h2d_bytes=s["h2d"], d2h_bytes=s["d2h"], polls=s["polls"], collect_cap=s["cap"], passes_per_poll=s["passes"])
+
     def submit(self, games, boards, last, clear=None):
         """Next roots of the players ``games`` (host arrays: boards int8[n,S,S], last int32[n], clear uint8[n])."""
         s = self._s

@@ -494,7 +494,7 @@ def run_ours(a):
         bp = BatchedPlayer(None, n_players=N, net=net, training=True, seed=1, game_id_base=rank * N,
                            eval_cache=shared_cache if shared_cache is not None else False,
                            board_size=S, simulation_per_step=sims, upper_simulation_per_step=upper)
-        bp.start_stream(boards, last, np.ones(N, np.uint8), passes=a.stream_passes, cap=int(os.environ.get('A5_STREAM_CAP', '0')) or None)
+        bp.start_stream(boards, last, np.ones(N, np.uint8), passes=a.stream_passes)
         bp.engine.tau().copy_(tau0)                              # Player.tau of the resumed games (a fresh Player starts at init_temp)
         desync_budgets(bp.engine, sims, 4321 + rank)             # (first search of every player only)
 
@@ -510,7 +510,7 @@ def run_ours(a):
 
         stream_until(2 * N)                                      # warm-up: tables built, budgets desynchronised
         st0 = bp.cache.stats() if bp.cache is not None else None
-        b0 = (bp._s["h2d"], bp._s["d2h"], bp._s["polls"])
+        b0 = bp.stream_stats()
         ec0 = bp.engine.counters()
         barrier()
         t0 = time.perf_counter()
@@ -525,14 +525,16 @@ def run_ours(a):
         else:
             got_all = float(got)
         e2e_val = got_all / t_stream
-        polls = bp._s["polls"] - b0[2]
+        b1 = bp.stream_stats()
+        polls = b1["polls"] - b0["polls"]
         ec1 = bp.engine.counters()
         steps_equiv = max(1e-9, got / N)                         # one "step" = N moves, as in the lock-step call
         e2e_stream = {"moves": got_all, "seconds": t_stream, "polls": polls, "passes_per_poll": a.stream_passes,
-                      "collect_cap": bp._s["cap"], "moves_per_poll": got / max(1, polls),
+                      "collect_cap": b1["collect_cap"], "moves_per_poll": got / max(1, polls),
                       "sims_per_move": (ec1["sims"] - ec0["sims"]) / max(1, ec1["moves"] - ec0["moves"]),
                       "passes_per_move_per_player": N * polls * a.stream_passes / max(1, got),
-                      "h2d_bytes_per_step": (bp._s["h2d"] - b0[0]) / steps_equiv, "d2h_bytes_per_step": (bp._s["d2h"] - b0[1]) / steps_equiv}
+                      "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) / steps_equiv,
+                      "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) / steps_equiv}
         if bp.cache is not None:
             st = bp.cache.stats()
             lk = max(1, st["lookups"] - st0["lookups"])
