@@ -903,8 +903,8 @@ __global__ void __launch_bounds__(WPB * 32) k_finish_move(const __grid_constant_
 }
 
 // Continuous batching of get_action calls (auto_play = 0; a5_engine_collect_moves / a5_engine_submit_roots).
-// The budget rule (player.py:140-143) gives re-used trees fewer simulations, so the searches of a batch end in
-// different passes.  k_collect_moves closes every search that has ended since the last call -- calc_policy
+// The searches of a batch end in different passes (budget rule of player.py:140-143 on re-used trees, terminal
+// simulations that run two to a pass, leaves deferred by the evaluation cache).  k_collect_moves closes every search that has ended since the last call -- calc_policy
 // (player.py:84-126), utils.step and utils.is_game_over of the played position -- into a compact row and parks the
 // game (active = 0) until k_submit_roots gives it its next root; the other games keep searching in between.
 template <int NCH>

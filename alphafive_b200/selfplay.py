@@ -337,9 +337,10 @@ class BatchedPlayer:
 
     # ---- continuous batching: searches are collected as they end, the other players keep searching -----------
     def start_stream(self, boards, last, clear=None, passes=4, cap=None):
-        """Continuous form of ``get_actions``.  The budget rule (player.py:140-143) gives re-used trees fewer
-        simulations, so the searches of a batch end in different passes; ``get_actions`` returns when the slowest is
-        done, the reference's players are independent objects and never wait for each other.  Here every player gets
+        """Continuous form of ``get_actions``.  The searches of a batch end in different passes (the budget rule of
+        player.py:140-143 cuts re-used trees short, simulations that end in terminal positions run two to a pass, leaves
+        deferred by the evaluation cache wait a pass); ``get_actions`` returns when the slowest is done, the
+        reference's players are independent objects and never wait for each other.  Here every player gets
         its root (host arrays as in ``get_actions``), then the caller alternates
 
             games, policy, action, nxt, codes = bp.poll()      # searches that have ended (host arrays)

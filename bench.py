@@ -598,7 +598,7 @@ def run_ours(a):
                      "api": "BatchedPlayer.start_stream / poll / submit (continuous batching over a5_engine_collect_moves / "
                             "a5_engine_submit_roots): the searches that have ended are read back to the host (policy, action, "
                             "next position, terminal code), the host restarts finished games and sends the next roots, the other "
-                            "players keep searching; positions from the lock-step run (tree reuse, budget rule, restarts); one "
+                            "players keep searching; positions and temperatures from the lock-step run (tree reuse, restarts); one "
                             "step = as many moves as there are players",
                      "stream": e2e_stream,
                      "lockstep_call": {"value": e2e_lock, "unit": "moves/s", "h2d_bytes_per_step": bp_bytes[0], "d2h_bytes_per_step": bp_bytes[1],

@@ -145,9 +145,12 @@ int a5_engine_busy(a5_engine* e, int32_t* h_busy, void* stream);
  * None), d_action int32[N] flat cell. */
 int a5_engine_finish_move(a5_engine* e, float* d_policy, int32_t* d_action, void* stream);
 
-/* Continuous batching of get_action calls (auto_play = 0).  The budget rule (player.py:140-143) gives
- * re-used trees fewer simulations, so the searches of a batch end in different passes; the reference's
- * players are independent objects and none of them waits for another (each worker of main.py:50-55 calls
+/* Continuous batching of get_action calls (auto_play = 0).  The searches of a batch end in different
+ * passes: the budget rule (player.py:140-143) gives re-used trees fewer simulations (a trained net
+ * concentrates the visits on the move that gets played), simulations that end in terminal positions run
+ * two to a pass, leaves deferred by the evaluation cache wait a pass, and roots arrive at different
+ * times; the reference's players are independent objects and none of them waits for another (each
+ * worker of main.py:50-55 calls
  * get_action on its own).  a5_engine_collect_moves closes every search that has ended and has not been
  * collected yet -- Player.calc_policy (player.py:84-126), then utils.step (utils.py:275-283) and
  * utils.is_game_over (utils.py:199-235) of the played position -- into compact rows:
